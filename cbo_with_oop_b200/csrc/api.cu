@@ -1,0 +1,148 @@
+// extern "C" surface of libcbo_b200.so (declared in include/cbo_b200.h).  No torch types, no exceptions, no
+// allocation: plain pointers and sizes in, status code out.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stddef.h>
+
+#include "cbo_common.cuh"
+
+namespace cbo {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    return (int)e;
+}
+
+int prior_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("CBO_PRIOR_VARIANT");
+        v = e ? atoi(e) : 0;
+        if (v < 0 || v > 2) v = 0;
+    }
+    return v;
+}
+
+int validate_sets(const cbo_set_desc* h_sets, int num_sets) {
+    CBO_REQUIRE(h_sets != nullptr, "descriptor array is NULL");
+    CBO_REQUIRE(num_sets >= 1 && num_sets <= 4096, "num_sets=%d outside [1,4096]", num_sets);
+    for (int s = 0; s < num_sets; ++s) {
+        const cbo_set_desc& S = h_sets[s];
+        CBO_REQUIRE(S.d >= 1 && S.d <= CBO_MAX_D, "set %d: d=%d outside [1,%d]", s, S.d, CBO_MAX_D);
+        CBO_REQUIRE(S.c >= 0 && S.c <= CBO_MAX_C, "set %d: c=%d outside [0,%d]", s, S.c, CBO_MAX_C);
+        CBO_REQUIRE(S.n_int >= 1 && S.n_int <= CBO_MAX_NINT, "set %d: n_int=%d outside [1,%d]", s, S.n_int, CBO_MAX_NINT);
+        long long g = 1;
+        for (int k = 0; k < S.d; ++k) {
+            CBO_REQUIRE(S.p[k] >= 1, "set %d: p[%d]=%d < 1", s, k, S.p[k]);
+            g *= S.p[k];
+        }
+        CBO_REQUIRE(g == S.g_total, "set %d: g_total=%lld != prod p = %lld", s, (long long)S.g_total, g);
+        CBO_REQUIRE(S.g_begin >= 0 && S.g_count >= 0 && S.g_begin + S.g_count <= S.g_total,
+                    "set %d: slice [%lld,+%lld) outside the grid of %lld", s, (long long)S.g_begin, (long long)S.g_count, g);
+        if (S.causal) {
+            CBO_REQUIRE(S.n_obs >= 1 && S.n_obs_pad >= S.n_obs && S.n_obs_pad % CBO_NPAD == 0,
+                        "set %d: n_obs=%d n_obs_pad=%d (pad must be a multiple of %d)", s, S.n_obs, S.n_obs_pad, CBO_NPAD);
+            CBO_REQUIRE(S.c == 0 || (S.n_mc >= 1 && S.n_mc_pad >= S.n_mc && S.n_mc_pad % CBO_SPAD == 0),
+                        "set %d: n_mc=%d n_mc_pad=%d (pad must be a multiple of %d)", s, S.n_mc, S.n_mc_pad, CBO_SPAD);
+            for (int k = 0; k < S.d; ++k) CBO_REQUIRE(S.ls_int[k] > 0.0, "set %d: ls_int[%d] must be positive", s, k);
+            for (int k = 0; k < S.c; ++k) CBO_REQUIRE(S.ls_cond[k] > 0.0, "set %d: ls_cond[%d] must be positive", s, k);
+        }
+        CBO_REQUIRE(S.cost_fix > 0.0 || S.cost_variable, "set %d: cost would be zero", s);
+    }
+    return 0;
+}
+
+int build_tables_impl(const cbo_set_desc*, int, cudaStream_t);
+int prior_precompute_impl(const cbo_set_desc*, int, cudaStream_t);
+int prior_eval_impl(const cbo_set_desc*, const cbo_set_desc*, int, int, cudaStream_t);
+int posterior_fit_impl(const cbo_set_desc*, const cbo_set_desc*, int, cudaStream_t);
+int sweep_impl(const cbo_set_desc*, const cbo_set_desc*, int, double, int, cbo_set_best*, cbo_set_best*, cbo_sweep_result*,
+               cudaStream_t);
+int argmax_combine_impl(const cbo_set_best*, int, int, cbo_set_best*, cbo_sweep_result*, cudaStream_t);
+
+}  // namespace cbo
+
+using namespace cbo;
+
+extern "C" {
+
+int cbo_abi_version(void) { return CBO_ABI_VERSION; }
+size_t cbo_sizeof_set_desc(void) { return sizeof(cbo_set_desc); }
+const char* cbo_last_error(void) { return g_error; }
+
+long cbo_offsetof_set_desc(const char* field) {
+    if (!field) return -1;
+#define F(name) if (strcmp(field, #name) == 0) return (long)offsetof(cbo_set_desc, name);
+    F(d) F(c) F(n_obs) F(n_obs_pad) F(n_mc) F(n_mc_pad) F(n_int) F(causal) F(p) F(g_total) F(g_begin) F(g_count)
+    F(x_obs_int) F(x_obs_cond) F(mc_cond) F(alpha_obs) F(kyinv) F(ls_int) F(ls_cond) F(s2) F(noise)
+    F(tab) F(u_int) F(P) F(pbar) F(w) F(M) F(grid) F(x_int) F(y_int) F(m_int) F(v_int) F(L) F(alpha) F(sqrt_v_int)
+    F(fit_info) F(cost_fix) F(cost_variable) F(reserved0) F(m) F(v) F(mu) F(var) F(ei) F(acq)
+#undef F
+    return -1;
+}
+
+long cbo_sweep_num_items(const cbo_set_desc* h_sets, int num_sets) {
+    if (!h_sets || num_sets < 0) return -1;
+    long long t = 0;
+    for (int s = 0; s < num_sets; ++s) t += host_items(h_sets[s], kItemsSweep);
+    return (long)t;
+}
+
+int cbo_build_tables(const cbo_set_desc* h_sets, int num_sets, void* stream) {
+    if (int rc = validate_sets(h_sets, num_sets)) return rc;
+    return build_tables_impl(h_sets, num_sets, (cudaStream_t)stream);
+}
+
+int cbo_prior_precompute(const cbo_set_desc* h_sets, int num_sets, void* stream) {
+    if (int rc = validate_sets(h_sets, num_sets)) return rc;
+    return prior_precompute_impl(h_sets, num_sets, (cudaStream_t)stream);
+}
+
+int cbo_prior_eval(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_sets, int which, void* stream) {
+    if (int rc = validate_sets(h_sets, num_sets)) return rc;
+    CBO_REQUIRE(d_sets != nullptr, "cbo_prior_eval: d_sets is NULL");
+    CBO_REQUIRE(which == 0 || which == 1, "cbo_prior_eval: which=%d must be 0 (grid) or 1 (x_int)", which);
+    for (int s = 0; s < num_sets; ++s) {
+        const cbo_set_desc& S = h_sets[s];
+        if (!S.causal) continue;
+        CBO_REQUIRE(S.M && S.w, "cbo_prior_eval: set %d has NULL M/w", s);
+        if (which == 0) {
+            CBO_REQUIRE(S.g_count == 0 || (S.m && S.v), "cbo_prior_eval: set %d has NULL m/v", s);
+            for (int k = 0; k < S.d; ++k) CBO_REQUIRE(S.tab[k], "cbo_prior_eval: set %d tab[%d] is NULL", s, k);
+        } else {
+            CBO_REQUIRE(S.u_int && S.m_int && S.v_int, "cbo_prior_eval: set %d has NULL u_int/m_int/v_int", s);
+        }
+    }
+    return prior_eval_impl(h_sets, d_sets, num_sets, which, (cudaStream_t)stream);
+}
+
+int cbo_posterior_fit(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_sets, void* stream) {
+    if (int rc = validate_sets(h_sets, num_sets)) return rc;
+    CBO_REQUIRE(d_sets != nullptr, "cbo_posterior_fit: d_sets is NULL");
+    return posterior_fit_impl(h_sets, d_sets, num_sets, (cudaStream_t)stream);
+}
+
+int cbo_sweep(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_sets, double best, int task_sign,
+              cbo_set_best* d_tile_best, cbo_set_best* d_set_best, cbo_sweep_result* d_result, void* stream) {
+    if (int rc = validate_sets(h_sets, num_sets)) return rc;
+    CBO_REQUIRE(d_sets != nullptr, "cbo_sweep: d_sets is NULL");
+    return sweep_impl(h_sets, d_sets, num_sets, best, task_sign, d_tile_best, d_set_best, d_result, (cudaStream_t)stream);
+}
+
+int cbo_argmax_combine(const cbo_set_best* d_gathered, int num_ranks, int num_sets, cbo_set_best* d_set_best,
+                       cbo_sweep_result* d_result, void* stream) {
+    CBO_REQUIRE(d_set_best && d_result, "cbo_argmax_combine: NULL output pointer");
+    return argmax_combine_impl(d_gathered, num_ranks, num_sets, d_set_best, d_result, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,89 @@
+// Shared device/host helpers for libcbo_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+
+#include "../../include/cbo_b200.h"
+
+namespace cbo {
+
+// ---- error plumbing (thread-local string, no exceptions across the ABI) ---------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define CBO_REQUIRE(cond, ...)                         \
+    do {                                               \
+        if (!(cond)) {                                 \
+            ::cbo::set_error(__VA_ARGS__);             \
+            return -1;                                 \
+        }                                              \
+    } while (0)
+
+#define CBO_CUDA(call)                                                \
+    do {                                                              \
+        cudaError_t e__ = (call);                                     \
+        if (e__ != cudaSuccess) return ::cbo::cuda_fail(e__, #call);  \
+    } while (0)
+
+int validate_sets(const cbo_set_desc* h_sets, int num_sets);
+
+// Work-item kinds of the batched kernels.  Every batched launch is a flat list of items
+// (set 0 tiles, set 1 tiles, ...); host and device count them with the same function.
+enum { kItemsPriorGrid = 0, kItemsPriorTrain = 1, kItemsSweep = 2 };
+__host__ __device__ inline long long host_items(const cbo_set_desc& S, int kind) {
+    if (kind == kItemsPriorGrid) return S.causal ? (S.g_count + CBO_PRIOR_TILE - 1) / CBO_PRIOR_TILE : 0;
+    if (kind == kItemsPriorTrain) return S.causal ? (S.n_int + CBO_PRIOR_TILE - 1) / CBO_PRIOR_TILE : 0;
+    return (S.g_count + CBO_SWEEP_TILE - 1) / CBO_SWEEP_TILE;
+}
+
+// ---- device helpers --------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// D(8x8) += A(8x4) * B(4x8), FP64 tensor pipe (SASS: DMMA.8x8x4).  Fragment ownership (lane = 4*g + t):
+//   a = A[g][t]     b = B[t][g]     c0,c1 = C[g][2t], C[g][2t+1]
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ double warp_sum(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+
+// (value, index) ordering used everywhere an argmax is reduced: larger value wins, ties go to the
+// smaller index; NaN never wins (callers map NaN to -inf first).  Matches np.argmax (first maximum).
+__device__ __forceinline__ bool better(double v, long long i, double bv, long long bi) {
+    return (v > bv) || (v == bv && i < bi);
+}
+
+// Map a flat work-item id to (set, tile inside the set) by scanning the descriptors (<= a few dozen sets).
+__device__ __forceinline__ int find_item(const cbo_set_desc* __restrict__ sets, int num_sets, int kind, int item,
+                                         int& tile) {
+    int base = 0, s = 0;
+    for (; s < num_sets - 1; ++s) {
+        const int c = (int)host_items(sets[s], kind);
+        if (item < base + c) break;
+        base += c;
+    }
+    tile = item - base;
+    return s;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace cbo

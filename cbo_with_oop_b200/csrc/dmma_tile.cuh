@@ -1,0 +1,49 @@
+// FP64 tensor-pipe (DMMA.8x8x4) tile machinery shared by the prior-precompute SYRK (K1a) and the
+// prior quadratic form (K1b).
+//
+// Both operands of C[m][n] += sum_k A[m][k] * B[n][k] are "k-contiguous row" matrices.  A BK=16 deep
+// slab of ROWS rows is kept in shared memory in FRAGMENT ORDER  [kb = k/4][row][k%4]  so that the
+// fragment of one 8-row block for one k4-step is 32 consecutive doubles: every warp-wide LDS.64 is
+// conflict-free (2 wavefronts for 256 B, the minimum), and a global row segment of 4 doubles lands as one
+// 32-byte unit -- cp.async 16-byte chunks map straight onto it without a transposing pass.
+#pragma once
+#include "cbo_common.cuh"
+
+namespace cbo {
+
+constexpr int kBK = 16;  // k depth of one pipeline stage
+
+__device__ __forceinline__ int frag_off(int rows, int kb, int r, int kk) { return ((kb * rows + r) << 2) + kk; }
+
+// Asynchronously copy ROWS x 16 doubles (global row pitch `ld`, 16-byte aligned) into a fragment-order slab.
+template <int ROWS, int NT>
+__device__ __forceinline__ void load_rows_async(double* slab, const double* __restrict__ g, size_t ld, int tid) {
+    constexpr int CH = kBK / 2;  // 16-byte chunks per row
+    static_assert((ROWS * CH) % NT == 0, "slab must divide evenly over the CTA");
+#pragma unroll
+    for (int it = 0; it < ROWS * CH / NT; ++it) {
+        const int idx = tid + it * NT;
+        const int r = idx / CH, ch = idx % CH;
+        cp_async16(slab + frag_off(ROWS, ch >> 1, r, (ch & 1) * 2), g + (size_t)r * ld + ch * 2);
+    }
+}
+
+// One pipeline stage of the warp-tiled product: warp (wm, wn) owns MA x NB blocks of 8x8.
+template <int BM, int BN, int MA, int NB>
+__device__ __forceinline__ void mma_stage(const double* __restrict__ sA, const double* __restrict__ sB,
+                                          double (&acc)[MA][NB][2], int row0, int col0, int lane) {
+#pragma unroll
+    for (int kb = 0; kb < kBK / 4; ++kb) {
+        double a[MA], b[NB];
+#pragma unroll
+        for (int mi = 0; mi < MA; ++mi) a[mi] = sA[((kb * BM + row0 + mi * 8) << 2) + lane];
+#pragma unroll
+        for (int ni = 0; ni < NB; ++ni) b[ni] = sB[((kb * BN + col0 + ni * 8) << 2) + lane];
+#pragma unroll
+        for (int mi = 0; mi < MA; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < NB; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+    }
+}
+
+}  // namespace cbo

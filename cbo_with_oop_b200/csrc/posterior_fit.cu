@@ -1,0 +1,144 @@
+// K2 -- batched exact-GP fit of the per-set surrogate, one CTA per exploration set, everything resident in
+// shared memory.
+//
+// Replaces GPRegression(...) at GaussianProcessFactory.py:57-73, i.e. GPy's ExactGaussianInference:
+//   causal     : K = exp(-.5 r^2) + sqrt(v(X)) sqrt(v(X))^T   (CausalRBF.K, causal_kernels.py:45-62; l = 1, s2 = 1)
+//                resid = y - m(X)                              (Mapping.f = mean function, :65-68)
+//   non-causal : K = exp(-.5 r^2), resid = y                   (:57-60)
+//   Ky = K + (1e-10 + 1e-8) I ; L = jitchol(Ky) ; alpha = Ky^-1 resid
+// jitchol rule (GPy util.linalg): plain Cholesky first; on a non-positive pivot retry with
+// jitter = mean(diag Ky) * 1e-6 * 10^t, t = 0..4; give up after 5 retries (fit_info[1] = 1, outputs NaN).
+// n <= 128, so the matrix (<= 128 KB) lives in shared memory; latency-bound by construction (n is tiny),
+// its cost is microseconds per trial.  r^2 is formed from coordinate differences (no cancellation).
+#include "cbo_common.cuh"
+
+namespace cbo {
+
+constexpr int kFitThreads = 256;
+
+__global__ void __launch_bounds__(kFitThreads, 1)
+posterior_fit_kernel(const cbo_set_desc* __restrict__ sets) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const cbo_set_desc& S = sets[blockIdx.x];
+    const int n = S.n_int, d = S.d, tid = threadIdx.x;
+    if (n <= 0) return;
+    double* A = reinterpret_cast<double*>(smem_raw);  // n x n, row-major, lower triangle becomes L
+    double* sv = A + (size_t)n * n;                   // sqrt(v_int)
+    double* rhs = sv + n;                             // y - m, then the solution
+    double* xs = rhs + n;                             // x_int copy, n x d
+    __shared__ int fail;
+    __shared__ double diag_mean;
+
+    for (int i = tid; i < n; i += kFitThreads) {
+        sv[i] = S.causal ? sqrt(S.v_int[i]) : 0.0;
+        rhs[i] = S.causal ? S.y_int[i] - S.m_int[i] : S.y_int[i];
+    }
+    for (int i = tid; i < n * d; i += kFitThreads) xs[i] = S.x_int[i];
+    __syncthreads();
+
+    int tries = 0;
+    double jitter = 0.0;
+    for (;;) {
+        // Gram matrix + noise (+ jitter on retries)
+        for (int e = tid; e < n * n; e += kFitThreads) {
+            const int i = e / n, j = e % n;
+            double r2 = 0.0;
+            for (int k = 0; k < d; ++k) {
+                const double t = xs[i * d + k] - xs[j * d + k];
+                r2 += t * t;
+            }
+            double kij = exp(-0.5 * r2) + sv[i] * sv[j];
+            if (i == j) kij += (1e-10 + 1e-8) + jitter;
+            A[e] = kij;
+        }
+        if (tid == 0) fail = 0;
+        __syncthreads();
+        if (tries == 0) {  // mean of the diagonal of Ky, the scale of GPy's jitter
+            if (tid == 0) {
+                double t = 0.0;
+                for (int i = 0; i < n; ++i) t += A[i * n + i];
+                diag_mean = t / n;
+            }
+            __syncthreads();
+        }
+        // right-looking Cholesky, lower
+        for (int j = 0; j < n; ++j) {
+            if (tid == 0) {
+                const double piv = A[j * n + j];
+                if (!(piv > 0.0)) fail = 1;
+                A[j * n + j] = sqrt(piv);
+            }
+            __syncthreads();
+            if (fail) break;
+            const double inv = 1.0 / A[j * n + j];
+            for (int i = j + 1 + tid; i < n; i += kFitThreads) A[i * n + j] *= inv;
+            __syncthreads();
+            const int rem = n - 1 - j;  // trailing update of the lower triangle
+            for (int e = tid; e < rem * rem; e += kFitThreads) {
+                const int i = j + 1 + e / rem, k = j + 1 + e % rem;
+                if (k <= i) A[i * n + k] -= A[i * n + j] * A[k * n + j];
+            }
+            __syncthreads();
+        }
+        if (!fail) break;
+        __syncthreads();
+        if (tries == 5) break;
+        jitter = (tries == 0) ? diag_mean * 1e-6 : jitter * 10.0;
+        ++tries;
+    }
+    const bool bad = fail != 0;
+    __syncthreads();
+
+    if (!bad) {
+        // forward L z = rhs, backward L^T a = z (n is tiny: one thread walks the recurrence, the CTA does the updates)
+        for (int j = 0; j < n; ++j) {
+            if (tid == 0) rhs[j] /= A[j * n + j];
+            __syncthreads();
+            const double zj = rhs[j];
+            for (int i = j + 1 + tid; i < n; i += kFitThreads) rhs[i] -= A[i * n + j] * zj;
+            __syncthreads();
+        }
+        for (int j = n - 1; j >= 0; --j) {
+            if (tid == 0) rhs[j] /= A[j * n + j];
+            __syncthreads();
+            const double aj = rhs[j];
+            for (int i = tid; i < j; i += kFitThreads) rhs[i] -= A[j * n + i] * aj;
+            __syncthreads();
+        }
+    }
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int e = tid; e < n * n; e += kFitThreads) {
+        const int i = e / n, j = e % n;
+        S.L[e] = bad ? nan : (j <= i ? A[e] : 0.0);
+    }
+    for (int i = tid; i < n; i += kFitThreads) {
+        S.alpha[i] = bad ? nan : rhs[i];
+        S.sqrt_v_int[i] = sv[i];
+    }
+    if (tid == 0) {
+        S.fit_info[0] = tries;
+        S.fit_info[1] = bad ? 1 : 0;
+    }
+}
+
+int posterior_fit_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_sets, cudaStream_t st) {
+    int nmax = 0;
+    for (int s = 0; s < num_sets; ++s) {
+        const cbo_set_desc& S = h_sets[s];
+        CBO_REQUIRE(S.n_int >= 1 && S.n_int <= CBO_MAX_NINT, "cbo_posterior_fit: set %d n_int=%d outside [1,%d]", s, S.n_int, CBO_MAX_NINT);
+        CBO_REQUIRE(S.x_int && S.y_int && S.L && S.alpha && S.sqrt_v_int && S.fit_info, "cbo_posterior_fit: set %d has a NULL pointer", s);
+        CBO_REQUIRE(!S.causal || (S.m_int && S.v_int), "cbo_posterior_fit: causal set %d needs m_int/v_int", s);
+        if (S.n_int > nmax) nmax = S.n_int;
+    }
+    const size_t smem = ((size_t)nmax * nmax + 2 * (size_t)nmax + (size_t)nmax * CBO_MAX_D) * sizeof(double);
+    static size_t configured = 0;
+    if (smem > configured) {
+        CBO_CUDA(cudaFuncSetAttribute(posterior_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    posterior_fit_kernel<<<num_sets, kFitThreads, smem, st>>>(d_sets);
+    CBO_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace cbo

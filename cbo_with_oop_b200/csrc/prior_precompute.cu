@@ -1,0 +1,187 @@
+// K1a -- fold the Monte-Carlo average of the causal prior into (w, M), once per observation.
+//
+// The reference averages observational-GP predictions over the conditioning samples for EVERY candidate
+// (DoCalculus.py:50-66 -> compute_do :68-78).  With P_ji = prod_{k not intervened} exp(-.5 ((C_ik - X_jk)/l_k)^2)
+// (train row j, conditioning sample i) that average is a fixed linear / quadratic form in u(x):
+//     pbar = mean_i P           w = s2 * alpha * pbar
+//     M    = s2^2 * Kyinv o (P P^T / S_mc)
+// so it is computed once here.  Two kernels per set, stream-ordered:
+//   pgen : P (N x S) with one exp per element, coalesced along i, deterministic row sums -> pbar, w
+//   syrk : lower block triangle of P P^T on the FP64 tensor pipe (DMMA), fused Hadamard with Kyinv,
+//          mirrored store so M is a full symmetric matrix.
+// Roofline: FP64 pipe, 2 N^2 S_mc dense-counted flops (N^2 S_mc executed).  No conditioning columns (c == 0)
+// degenerates to M = s2^2 Kyinv.
+#include "dmma_tile.cuh"
+
+namespace cbo {
+
+struct CondParams {
+    double il[CBO_MAX_C];
+};
+
+__global__ void __launch_bounds__(256)
+pgen_kernel(const double* __restrict__ x_obs_cond, const double* __restrict__ mc_cond, int c, int n_obs, int n_mc,
+            int n_mc_pad, CondParams cp, const double* __restrict__ alpha_obs, double s2, double* __restrict__ P,
+            double* __restrict__ pbar, double* __restrict__ w) {
+    __shared__ double red[8];
+    const int j = blockIdx.x;  // 0 .. n_obs_pad-1
+    double* __restrict__ row = P + (size_t)j * n_mc_pad;
+    const bool live = j < n_obs;
+    double xj[CBO_MAX_C];
+#pragma unroll
+    for (int k = 0; k < CBO_MAX_C; ++k) xj[k] = (live && k < c) ? x_obs_cond[(size_t)k * n_obs + j] : 0.0;
+    double sum = 0.0;
+    for (int i = threadIdx.x; i < n_mc_pad; i += 256) {
+        double val = 0.0;
+        if (live && i < n_mc) {
+            double r2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < CBO_MAX_C; ++k) {
+                if (k < c) {
+                    const double t = (mc_cond[(size_t)k * n_mc + i] - xj[k]) * cp.il[k];
+                    r2 += t * t;
+                }
+            }
+            val = exp(-0.5 * r2);
+        }
+        row[i] = val;
+        sum += val;
+    }
+    sum = warp_sum(sum);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int x = 0; x < 8; ++x) t += red[x];
+        const double pb = live ? t / (double)n_mc : 0.0;
+        pbar[j] = pb;
+        w[j] = live ? s2 * alpha_obs[j] * pb : 0.0;
+    }
+}
+
+// c == 0: P == 1, pbar == 1, Q == 1.
+__global__ void __launch_bounds__(256)
+nocond_kernel(const double* __restrict__ kyinv, const double* __restrict__ alpha_obs, int n_obs, int n_obs_pad, double s2,
+              double* __restrict__ M, double* __restrict__ pbar, double* __restrict__ w) {
+    const int j = blockIdx.y;
+    const bool lj = j < n_obs;
+    for (int k = blockIdx.x * 256 + threadIdx.x; k < n_obs_pad; k += gridDim.x * 256) {
+        M[(size_t)j * n_obs_pad + k] = (lj && k < n_obs) ? (s2 * s2) * kyinv[(size_t)j * n_obs + k] : 0.0;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        pbar[j] = lj ? 1.0 : 0.0;
+        w[j] = lj ? s2 * alpha_obs[j] : 0.0;
+    }
+}
+
+template <int WM, int WN, int MA, int NB, int STAGES>
+__global__ void __launch_bounds__(WM * WN * 32, 1)
+syrk_kernel(const double* __restrict__ P, int n_mc_pad, const double* __restrict__ kyinv, int n_obs, int n_obs_pad,
+            double coef, double* __restrict__ M) {
+    constexpr int BM = WM * MA * 8, BN = WN * NB * 8, NT = WM * WN * 32;
+    static_assert(BM == BN && BM == CBO_NPAD, "square tiles of CBO_NPAD");
+    constexpr int TILE = BM * kBK;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* sA = reinterpret_cast<double*>(smem_raw);
+    double* sB = sA + STAGES * TILE;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp / WN, wn = warp % WN;
+    const int row0 = wm * MA * 8, col0 = wn * NB * 8;
+
+    // lower-triangular tile pair (bi >= bj) from the linear block index
+    const int t = blockIdx.x;
+    int bi = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((long long)bi * (bi + 1) / 2 > t) --bi;
+    while ((long long)(bi + 1) * (bi + 2) / 2 <= t) ++bi;
+    const int bj = t - bi * (bi + 1) / 2;
+
+    const double* __restrict__ gA = P + (size_t)bi * BM * n_mc_pad;
+    const double* __restrict__ gB = P + (size_t)bj * BN * n_mc_pad;
+    const int nk = n_mc_pad / kBK;
+
+    double acc[MA][NB][2];
+#pragma unroll
+    for (int mi = 0; mi < MA; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NB; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+#pragma unroll 1
+    for (int i = 0; i < STAGES - 1; ++i) {
+        if (i < nk) {
+            load_rows_async<BM, NT>(sA + i * TILE, gA + (size_t)i * kBK, n_mc_pad, tid);
+            load_rows_async<BN, NT>(sB + i * TILE, gB + (size_t)i * kBK, n_mc_pad, tid);
+        }
+        cp_async_commit();
+    }
+#pragma unroll 1
+    for (int kt = 0; kt < nk; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        const int nx = kt + STAGES - 1;
+        if (nx < nk) {
+            const int ps = nx % STAGES;
+            load_rows_async<BM, NT>(sA + ps * TILE, gA + (size_t)nx * kBK, n_mc_pad, tid);
+            load_rows_async<BN, NT>(sB + ps * TILE, gB + (size_t)nx * kBK, n_mc_pad, tid);
+        }
+        cp_async_commit();
+        const int cs = kt % STAGES;
+        mma_stage<BM, BN, MA, NB>(sA + cs * TILE, sB + cs * TILE, acc, row0, col0, lane);
+    }
+    cp_async_wait<0>();
+
+    // M = coef * Kyinv o Q, zero outside the live N x N corner; mirrored into the upper triangle
+#pragma unroll
+    for (int mi = 0; mi < MA; ++mi) {
+        const int r = bi * BM + row0 + mi * 8 + (lane >> 2);
+#pragma unroll
+        for (int ni = 0; ni < NB; ++ni) {
+            const int cidx = bj * BN + col0 + ni * 8 + (lane & 3) * 2;
+            double v0 = 0.0, v1 = 0.0;
+            if (r < n_obs) {
+                if (cidx < n_obs) v0 = coef * kyinv[(size_t)r * n_obs + cidx] * acc[mi][ni][0];
+                if (cidx + 1 < n_obs) v1 = coef * kyinv[(size_t)r * n_obs + cidx + 1] * acc[mi][ni][1];
+            }
+            *reinterpret_cast<double2*>(M + (size_t)r * n_obs_pad + cidx) = make_double2(v0, v1);
+            if (bi != bj) {
+                M[(size_t)cidx * n_obs_pad + r] = v0;
+                M[(size_t)(cidx + 1) * n_obs_pad + r] = v1;
+            }
+        }
+    }
+}
+
+int prior_precompute_impl(const cbo_set_desc* h_sets, int num_sets, cudaStream_t st) {
+    constexpr int STAGES = 4;
+    constexpr size_t SMEM = (size_t)STAGES * 2 * CBO_NPAD * kBK * sizeof(double);
+    auto kern = syrk_kernel<2, 4, 8, 4, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        CBO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        configured = true;
+    }
+    for (int s = 0; s < num_sets; ++s) {
+        const cbo_set_desc& S = h_sets[s];
+        if (!S.causal) continue;
+        CBO_REQUIRE(S.kyinv && S.alpha_obs && S.M && S.w && S.pbar, "cbo_prior_precompute: set %d has a NULL pointer", s);
+        if (S.c == 0) {
+            nocond_kernel<<<dim3(8, S.n_obs_pad), 256, 0, st>>>(S.kyinv, S.alpha_obs, S.n_obs, S.n_obs_pad, S.s2, S.M, S.pbar, S.w);
+            CBO_CUDA(cudaGetLastError());
+            continue;
+        }
+        CBO_REQUIRE(S.P && S.x_obs_cond && S.mc_cond, "cbo_prior_precompute: set %d has a NULL P/x_obs_cond/mc_cond", s);
+        CondParams cp;
+        for (int k = 0; k < CBO_MAX_C; ++k) cp.il[k] = k < S.c ? 1.0 / S.ls_cond[k] : 0.0;
+        pgen_kernel<<<S.n_obs_pad, 256, 0, st>>>(S.x_obs_cond, S.mc_cond, S.c, S.n_obs, S.n_mc, S.n_mc_pad, cp, S.alpha_obs,
+                                                 S.s2, S.P, S.pbar, S.w);
+        CBO_CUDA(cudaGetLastError());
+        const int nT = S.n_obs_pad / CBO_NPAD;
+        const int tiles = nT * (nT + 1) / 2;
+        kern<<<tiles, 256, SMEM, st>>>(S.P, S.n_mc_pad, S.kyinv, S.n_obs, S.n_obs_pad, (S.s2 * S.s2) / (double)S.n_mc, S.M);
+        CBO_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+}  // namespace cbo

@@ -1,0 +1,252 @@
+// K3 + K4 -- posterior predict, Expected Improvement / cost and the first-argmax over every candidate.
+//
+// Per candidate x of set s (one thread each; L, alpha, X_I staged once per CTA in shared memory):
+//   k*_i = exp(-.5 |x - X_I,i|^2) + sqrt(v_I,i) sqrt(v(x))        CausalRBF.K(X_I, x), causal_kernels.py:55-62
+//   mu   = m(x) + k*.alpha                                           GPy PosteriorExact._raw_predict + mean function
+//   t    = L^-1 k*  (forward substitution) ; var = (1 + v(x)) - |t|^2 + 1e-10   Kdiag :64-79, dtrtrs, Gaussian noise
+//   EI   = sd (u Phi(u) + phi(u)), u = (best - mu) / sd, negated for task 'max'   causal_acquisition_functions.py:33-43,85-87
+//   acq  = EI / cost(x)                                              utils.py:34, cost_functions.py:11-17
+// then a (value, index) max-reduction with np.argmax semantics (first maximum; NaN counts as -inf and is
+// tallied), per tile -> per set -> global (CBO.select_next_intervention, CBO.py:269-277: first set attaining the max).
+// The variance is not clipped (the reference does not clip either); a negative variance gives NaN.
+// Roofline: with the prior cached this pass is 16 B/candidate of HBM reads plus n^2/2 FMAs; it is a few
+// per cent of a post-observation sweep and the whole of a post-intervention refresh.
+#include <float.h>
+#include "cbo_common.cuh"
+
+namespace cbo {
+
+constexpr int kSweepThreads = CBO_SWEEP_TILE;
+
+__global__ void __launch_bounds__(kSweepThreads)
+sweep_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, double best, double task_sign,
+             cbo_set_best* __restrict__ tile_best) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int tile;
+    const int s = find_item(sets, num_sets, kItemsSweep, blockIdx.x, tile);
+    const cbo_set_desc& S = sets[s];
+    const int n = S.n_int, d = S.d, tid = threadIdx.x;
+    const bool causal = S.causal != 0;
+
+    double* Lp = reinterpret_cast<double*>(smem_raw);  // packed lower triangle, row i at i(i+1)/2
+    double* al = Lp + (size_t)n * (n + 1) / 2;
+    double* sv = al + n;
+    double* xs = sv + n;                       // n x d
+    double* tcol = xs + (size_t)n * CBO_MAX_D;  // [n][kSweepThreads] forward-substitution workspace
+    __shared__ double red_v[kSweepThreads / 32];
+    __shared__ long long red_i[kSweepThreads / 32];
+    __shared__ int red_n[kSweepThreads / 32];
+
+    for (int e = tid; e < n * n; e += kSweepThreads) {
+        const int i = e / n, j = e % n;
+        if (j <= i) Lp[i * (i + 1) / 2 + j] = S.L[e];
+    }
+    for (int i = tid; i < n; i += kSweepThreads) {
+        al[i] = S.alpha[i];
+        sv[i] = causal ? S.sqrt_v_int[i] : 0.0;
+    }
+    for (int i = tid; i < n * d; i += kSweepThreads) xs[i] = S.x_int[i];
+    __syncthreads();
+
+    const long long loc = (long long)tile * kSweepThreads + tid;
+    const bool valid = loc < S.g_count;
+    const long long gidx = S.g_begin + loc;
+    double val = -DBL_MAX * 2.0;  // -inf
+    long long idx = LLONG_MAX;
+    int is_nan = 0;
+    if (valid) {
+        double x[CBO_MAX_D];
+        {
+            long long gg = gidx;
+#pragma unroll
+            for (int k = CBO_MAX_D - 1; k >= 0; --k) {
+                if (k < d) {
+                    const int i = (int)(gg % S.p[k]);
+                    gg /= S.p[k];
+                    x[k] = S.grid[k][i];
+                } else {
+                    x[k] = 0.0;
+                }
+            }
+        }
+        const double vg = causal ? S.v[loc] : 0.0;
+        const double mg = causal ? S.m[loc] : 0.0;
+        const double svg = causal ? sqrt(vg) : 0.0;
+        double mu = 0.0, ss = 0.0;
+        for (int i = 0; i < n; ++i) {
+            double r2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < CBO_MAX_D; ++k) {
+                if (k < d) {
+                    const double t = x[k] - xs[i * d + k];
+                    r2 += t * t;
+                }
+            }
+            const double ks = exp(-0.5 * r2) + sv[i] * svg;
+            mu = fma(ks, al[i], mu);
+            const double* __restrict__ Li = Lp + i * (i + 1) / 2;
+            double a = ks;
+            for (int j = 0; j < i; ++j) a = fma(-Li[j], tcol[j * kSweepThreads + tid], a);
+            const double t = a / Li[i];
+            tcol[i * kSweepThreads + tid] = t;
+            ss = fma(t, t, ss);
+        }
+        mu += mg;
+        const double var = ((1.0 + vg) - ss) + 1e-10;
+        const double sd = sqrt(var);
+        const double u = (best - mu) / sd;
+        const double pdf = 0.3989422804014326779 * exp(-0.5 * u * u);
+        const double cdf = 0.5 * erfc(-u * 0.7071067811865475244);
+        const double ei = task_sign * (sd * (u * cdf + pdf));
+        double cost = S.cost_fix;
+        if (S.cost_variable) {
+#pragma unroll
+            for (int k = 0; k < CBO_MAX_D; ++k)
+                if (k < d) cost += fabs(x[k]);
+        }
+        const double acq = ei / cost;
+        if (S.mu) S.mu[loc] = mu;
+        if (S.var) S.var[loc] = var;
+        if (S.ei) S.ei[loc] = ei;
+        if (S.acq) S.acq[loc] = acq;
+        is_nan = acq != acq;
+        val = is_nan ? val : acq;
+        idx = gidx;
+    }
+    // first-argmax over the tile
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, val, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (better(ov, oi, val, idx)) { val = ov; idx = oi; }
+    }
+    const int nn = __popc(__ballot_sync(0xffffffffu, is_nan));
+    if ((tid & 31) == 0) { red_v[tid >> 5] = val; red_i[tid >> 5] = idx; red_n[tid >> 5] = nn; }
+    __syncthreads();
+    if (tid == 0) {
+        int nan_total = red_n[0];
+        for (int x = 1; x < kSweepThreads / 32; ++x) {
+            if (better(red_v[x], red_i[x], val, idx)) { val = red_v[x]; idx = red_i[x]; }
+            nan_total += red_n[x];
+        }
+        cbo_set_best b;
+        b.value = val; b.index = idx; b.n_nan = nan_total; b.reserved = 0;
+        tile_best[blockIdx.x] = b;
+    }
+}
+
+// per-set reduction over the set's tiles (one CTA per set, fixed order)
+__global__ void __launch_bounds__(256)
+set_reduce_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, const cbo_set_best* __restrict__ tile_best,
+                  cbo_set_best* __restrict__ set_best) {
+    __shared__ double rv[8];
+    __shared__ long long ri[8];
+    __shared__ int rn[8];
+    const int s = blockIdx.x, tid = threadIdx.x;
+    long long base = 0;
+    for (int x = 0; x < s; ++x) base += host_items(sets[x], kItemsSweep);
+    const long long cnt = host_items(sets[s], kItemsSweep);
+    double val = -DBL_MAX * 2.0;
+    long long idx = LLONG_MAX;
+    int nn = 0;
+    for (long long t = tid; t < cnt; t += 256) {
+        const cbo_set_best b = tile_best[base + t];
+        if (better(b.value, b.index, val, idx)) { val = b.value; idx = b.index; }
+        nn += b.n_nan;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, val, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        nn += __shfl_xor_sync(0xffffffffu, nn, o);
+        if (better(ov, oi, val, idx)) { val = ov; idx = oi; }
+    }
+    if ((tid & 31) == 0) { rv[tid >> 5] = val; ri[tid >> 5] = idx; rn[tid >> 5] = nn; }
+    __syncthreads();
+    if (tid == 0) {
+        nn = rn[0];
+        for (int x = 1; x < 8; ++x) {
+            if (better(rv[x], ri[x], val, idx)) { val = rv[x]; idx = ri[x]; }
+            nn += rn[x];
+        }
+        cbo_set_best b;
+        b.value = val; b.index = (idx == LLONG_MAX) ? -1 : idx; b.n_nan = nn; b.reserved = 0;
+        set_best[s] = b;
+    }
+}
+
+// gathered[rank][set] -> set_best[set] (when num_ranks > 0) and the global result.
+// CBO.select_next_intervention (CBO.py:275-276): first set attaining the maximum.
+__global__ void __launch_bounds__(128)
+combine_kernel(const cbo_set_best* __restrict__ gathered, int num_ranks, int num_sets, cbo_set_best* __restrict__ set_best,
+               cbo_sweep_result* __restrict__ result) {
+    for (int s = threadIdx.x; s < num_sets && num_ranks > 0; s += blockDim.x) {
+        double val = -DBL_MAX * 2.0;
+        long long idx = LLONG_MAX;
+        int nn = 0;
+        for (int r = 0; r < num_ranks; ++r) {
+            const cbo_set_best b = gathered[(size_t)r * num_sets + s];
+            const long long bi = b.index < 0 ? LLONG_MAX : b.index;
+            if (better(b.value, bi, val, idx)) { val = b.value; idx = bi; }
+            nn += b.n_nan;
+        }
+        cbo_set_best o;
+        o.value = val; o.index = (idx == LLONG_MAX) ? -1 : idx; o.n_nan = nn; o.reserved = 0;
+        set_best[s] = o;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        cbo_sweep_result r;
+        r.value = -DBL_MAX * 2.0; r.index = -1; r.set = -1; r.n_nan = 0;
+        for (int s = 0; s < num_sets; ++s) {
+            const cbo_set_best b = set_best[s];
+            r.n_nan += b.n_nan;
+            if (b.index >= 0 && (r.set < 0 || b.value > r.value)) { r.value = b.value; r.index = b.index; r.set = s; }
+        }
+        *result = r;
+    }
+}
+
+int sweep_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_sets, double best, int task_sign,
+               cbo_set_best* d_tile_best, cbo_set_best* d_set_best, cbo_sweep_result* d_result, cudaStream_t st) {
+    CBO_REQUIRE(task_sign == 1 || task_sign == -1, "cbo_sweep: task_sign must be +1 ('min') or -1 ('max')");
+    CBO_REQUIRE(d_tile_best && d_set_best && d_result, "cbo_sweep: NULL output pointer");
+    long long total = 0;
+    int nmax = 1;
+    for (int s = 0; s < num_sets; ++s) {
+        const cbo_set_desc& S = h_sets[s];
+        CBO_REQUIRE(S.n_int >= 1 && S.n_int <= CBO_MAX_NINT, "cbo_sweep: set %d n_int=%d outside [1,%d]", s, S.n_int, CBO_MAX_NINT);
+        CBO_REQUIRE(S.L && S.alpha && S.x_int, "cbo_sweep: set %d has a NULL posterior pointer", s);
+        CBO_REQUIRE(!S.causal || (S.m && S.v && S.sqrt_v_int), "cbo_sweep: causal set %d needs m/v/sqrt_v_int", s);
+        for (int k = 0; k < S.d; ++k) CBO_REQUIRE(S.grid[k], "cbo_sweep: set %d grid[%d] is NULL", s, k);
+        total += host_items(S, kItemsSweep);
+        if (S.n_int > nmax) nmax = S.n_int;
+    }
+    CBO_REQUIRE(total < 2147483647LL, "cbo_sweep: too many work items");
+    if (total > 0) {
+        const size_t smem = ((size_t)nmax * (nmax + 1) / 2 + 2 * (size_t)nmax + (size_t)nmax * CBO_MAX_D +
+                             (size_t)nmax * kSweepThreads) * sizeof(double);
+        static size_t configured = 0;
+        if (smem > configured) {
+            CBO_CUDA(cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        sweep_kernel<<<(unsigned)total, kSweepThreads, smem, st>>>(d_sets, num_sets, best, (double)task_sign, d_tile_best);
+        CBO_CUDA(cudaGetLastError());
+    }
+    set_reduce_kernel<<<num_sets, 256, 0, st>>>(d_sets, num_sets, d_tile_best, d_set_best);
+    CBO_CUDA(cudaGetLastError());
+    combine_kernel<<<1, 128, 0, st>>>(nullptr, 0, num_sets, d_set_best, d_result);
+    CBO_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int argmax_combine_impl(const cbo_set_best* d_gathered, int num_ranks, int num_sets, cbo_set_best* d_set_best,
+                        cbo_sweep_result* d_result, cudaStream_t st) {
+    CBO_REQUIRE(d_gathered && num_ranks >= 1 && num_sets >= 1, "cbo_argmax_combine: bad arguments");
+    combine_kernel<<<1, 128, 0, st>>>(d_gathered, num_ranks, num_sets, d_set_best, d_result);
+    CBO_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace cbo

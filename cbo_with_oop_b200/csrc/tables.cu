@@ -1,0 +1,72 @@
+// K0 -- separable RBF factors of the observational GP's cross-covariance on the intervened columns.
+//
+//   tab[k][i][j] = exp(-.5 ((grid_k[i] - X_obs[j, k]) / l_k)^2)          i < p_k, j < N   (0 for N <= j < Npad)
+//   u_int[i][j]  = exp(-.5 sum_k ((x_int[i, k] - X_obs[j, k]) / l_k)^2)   i < n_int
+//
+// These are the k(Z_i(x), X_j) factors that the reference evaluates inside gp.predict for every candidate
+// (DoCalculus.py:77 via get_intervened_inputs :80-89).  On a tensor grid u(x) is the elementwise product of one
+// row per table, so the quadratic-form kernel never calls exp.  HBM-bound (one 8-byte store per exp),
+// coalesced along j; a negligible share of a sweep.
+#include "cbo_common.cuh"
+
+namespace cbo {
+
+__global__ void __launch_bounds__(256)
+table_kernel(const double* __restrict__ coords, int p, const double* __restrict__ xcol, int n_obs, int n_obs_pad,
+             double inv_l, double* __restrict__ out) {
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= n_obs_pad) return;
+    const bool live = j < n_obs;
+    const double x = live ? xcol[j] : 0.0;
+    for (int i = blockIdx.y; i < p; i += gridDim.y) {
+        const double t = (coords[i] - x) * inv_l;
+        out[(size_t)i * n_obs_pad + j] = live ? exp(-0.5 * (t * t)) : 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+points_table_kernel(const double* __restrict__ x_int, int n_int, int d, const double* __restrict__ x_obs_int, int n_obs,
+                    int n_obs_pad, double il0, double il1, double il2, double il3, double* __restrict__ out) {
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= n_obs_pad) return;
+    const bool live = j < n_obs;
+    const double il[CBO_MAX_D] = {il0, il1, il2, il3};
+    double x[CBO_MAX_D];
+#pragma unroll
+    for (int k = 0; k < CBO_MAX_D; ++k) x[k] = (live && k < d) ? x_obs_int[(size_t)k * n_obs + j] : 0.0;
+    for (int i = blockIdx.y; i < n_int; i += gridDim.y) {
+        double r2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < CBO_MAX_D; ++k) {
+            if (k < d) {
+                const double t = (x_int[i * d + k] - x[k]) * il[k];
+                r2 += t * t;
+            }
+        }
+        out[(size_t)i * n_obs_pad + j] = live ? exp(-0.5 * r2) : 0.0;
+    }
+}
+
+int build_tables_impl(const cbo_set_desc* h_sets, int num_sets, cudaStream_t st) {
+    for (int s = 0; s < num_sets; ++s) {
+        const cbo_set_desc& S = h_sets[s];
+        if (!S.causal) continue;
+        const unsigned gx = (S.n_obs_pad + 255) / 256;
+        for (int k = 0; k < S.d; ++k) {
+            CBO_REQUIRE(S.tab[k] && S.grid[k] && S.x_obs_int, "cbo_build_tables: set %d has a NULL table/grid pointer", s);
+            const unsigned gy = (unsigned)(S.p[k] < 1024 ? S.p[k] : 1024);
+            table_kernel<<<dim3(gx, gy), 256, 0, st>>>(S.grid[k], S.p[k], S.x_obs_int + (size_t)k * S.n_obs, S.n_obs,
+                                                       S.n_obs_pad, 1.0 / S.ls_int[k], S.tab[k]);
+        }
+        CBO_REQUIRE(S.u_int && S.x_int, "cbo_build_tables: set %d has a NULL u_int/x_int pointer", s);
+        const unsigned gy = (unsigned)(S.n_int < 1024 ? S.n_int : 1024);
+        points_table_kernel<<<dim3(gx, gy), 256, 0, st>>>(S.x_int, S.n_int, S.d, S.x_obs_int, S.n_obs, S.n_obs_pad,
+                                                          1.0 / S.ls_int[0], S.d > 1 ? 1.0 / S.ls_int[1] : 0.0,
+                                                          S.d > 2 ? 1.0 / S.ls_int[2] : 0.0,
+                                                          S.d > 3 ? 1.0 / S.ls_int[3] : 0.0, S.u_int);
+        CBO_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+}  // namespace cbo

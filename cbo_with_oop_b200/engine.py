@@ -1,0 +1,411 @@
+"""Host side of the B200 acquisition sweep: owns device memory (PyTorch tensors), builds the cbo_set_desc
+array, and drives libcbo_b200.so through its C ABI.  PyTorch is plumbing here (allocation, streams, NCCL);
+every number is produced by the hand-written kernels in csrc/.
+
+One SweepEngine = one rank's share of one trial's sweep over every exploration set.
+Stages (reference call sites in include/cbo_b200.h):
+    build_tables -> prior_precompute -> prior_eval(x_int) -> posterior_fit -> prior_eval(grid) -> sweep
+`sweep(best, task)` runs all of them (a post-observation trial); `refresh(best, task, refit=[...])` reuses the
+cached prior and only refits the listed sets (a post-intervention trial).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import SetBest, SetDesc, SweepResult
+from .partition import SetSize, partition
+
+
+@dataclass
+class SetProblem:
+    """Host description of one exploration set's share of a trial (all float64 NumPy, caller-owned)."""
+    x_obs_int: np.ndarray            # (N, d) intervened columns of the observational GP's training design
+    x_obs_cond: np.ndarray           # (N, c) conditioning columns (c may be 0)
+    mc_cond: np.ndarray              # (S_mc, c) conditioning samples (reference: the same observational rows)
+    alpha_obs: np.ndarray            # (N,)  Ky^-1 y of the observational GP
+    kyinv: np.ndarray                # (N, N) Ky^-1
+    ls_int: np.ndarray               # (d,) lengthscales of the intervened columns
+    ls_cond: np.ndarray              # (c,)
+    s2: float                        # RBF variance
+    grid: List[np.ndarray]           # d coordinate tables (np.linspace from the host)
+    x_int: np.ndarray                # (n, d) interventional inputs
+    y_int: np.ndarray                # (n,)   interventional outputs
+    noise: float = 1e-2              # utils.py:43
+    cost_fix: float = 1.0
+    cost_variable: bool = False
+    causal: bool = True
+    name: str = ""
+
+    @property
+    def d(self) -> int:
+        return len(self.grid)
+
+    @property
+    def g_total(self) -> int:
+        g = 1
+        for t in self.grid:
+            g *= len(t)
+        return g
+
+    @staticmethod
+    def non_causal(grid, x_int, y_int, cost_fix=1.0, cost_variable=False, name=""):
+        d = len(grid)
+        z = np.zeros((0, d))
+        return SetProblem(z, np.zeros((0, 0)), np.zeros((0, 0)), np.zeros(0), np.zeros((0, 0)), np.ones(d), np.zeros(0),
+                          1.0, list(grid), x_int, y_int, cost_fix=cost_fix, cost_variable=cost_variable, causal=False,
+                          name=name)
+
+
+@dataclass
+class SweepOutput:
+    set: int                 # global exploration-set index of the next intervention (-1: nothing evaluated)
+    index: int               # flat grid index inside that set
+    value: float             # acquisition value there
+    x: Optional[np.ndarray]  # (d,) coordinates
+    set_values: np.ndarray   # (S,) best acquisition per set (the reference's `ys`)
+    set_indices: np.ndarray  # (S,) flat index of each set's best candidate
+    n_nan: int
+    stage_ms: Dict[str, float] = field(default_factory=dict)
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class SweepEngine:
+    def __init__(self, problems: Sequence[SetProblem], device: str | torch.device = "cuda:0", rank: int = 0,
+                 world_size: int = 1, keep: Sequence[str] = (), process_group=None, n_int_capacity: int = _lib.CBO_MAX_NINT,
+                 pinned_staging: bool = False):
+        if not torch.cuda.is_available():
+            raise RuntimeError("SweepEngine needs a CUDA device: the CUDA library is the product, there is no CPU path")
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        self.rank, self.world = rank, world_size
+        self.group = process_group
+        self.problems = list(problems)
+        self.keep = tuple(keep)
+        self.ncap = int(n_int_capacity)
+        self.timing = False
+        self.pinned_staging = pinned_staging
+        for k in self.keep:
+            if k not in ("mu", "var", "ei", "acq"):
+                raise ValueError(f"unknown array {k!r}")
+        S = len(self.problems)
+        sizes = [SetSize(p.g_total, p.x_obs_int.shape[0] if p.causal else 0, p.x_int.shape[0]) for p in self.problems]
+        self.slices = partition(sizes, world_size)[rank]
+        self.active = [s for s in range(S) if self.slices[s][1] > 0]   # global ids of the sets this rank touches
+        self.local_of = {g: i for i, g in enumerate(self.active)}
+        self._alloc()
+        self.upload()
+
+    # ------------------------------------------------------------------------------------------------
+    def _dev(self, shape, dtype=torch.float64, zero=False):
+        f = torch.zeros if zero else torch.empty
+        return f(shape, dtype=dtype, device=self.device)
+
+    def _alloc(self):
+        A = len(self.active)
+        self.h_sets = (SetDesc * max(A, 1))()
+        self.buf: List[Dict[str, torch.Tensor]] = []
+        self.stage: List[Dict[str, torch.Tensor]] = []   # pinned host staging of the inputs (e2e path)
+        p_rows = p_cols = 0
+        for g in self.active:
+            pr = self.problems[g]
+            if pr.causal and pr.x_obs_cond.shape[1] > 0:
+                p_rows = max(p_rows, _round_up(pr.x_obs_int.shape[0], _lib.CBO_NPAD))
+                p_cols = max(p_cols, _round_up(pr.mc_cond.shape[0], _lib.CBO_SPAD))
+        self.P = self._dev((p_rows * p_cols,)) if p_rows else None
+        for li, g in enumerate(self.active):
+            pr = self.problems[g]
+            d, n = pr.d, pr.x_int.shape[0]
+            if n > self.ncap or self.ncap > _lib.CBO_MAX_NINT:
+                raise ValueError(f"set {g}: n_int={n} exceeds the capacity {self.ncap} (max {_lib.CBO_MAX_NINT})")
+            gb, gc = self.slices[g]
+            b: Dict[str, torch.Tensor] = {}
+            b["x_int"] = self._dev((self.ncap * d,))
+            b["y_int"] = self._dev((self.ncap,))
+            b["L"] = self._dev((self.ncap * self.ncap,))
+            b["alpha"] = self._dev((self.ncap,))
+            b["sqrt_v_int"] = self._dev((self.ncap,), zero=True)
+            b["m_int"] = self._dev((self.ncap,), zero=True)
+            b["v_int"] = self._dev((self.ncap,), zero=True)
+            b["fit_info"] = self._dev((2,), dtype=torch.int32, zero=True)
+            for k in range(d):
+                b[f"grid{k}"] = self._dev((len(pr.grid[k]),))
+            for name in self.keep:
+                b[name] = self._dev((gc,))
+            if pr.causal:
+                N, c, Smc = pr.x_obs_int.shape[0], pr.x_obs_cond.shape[1], pr.mc_cond.shape[0]
+                Np = _round_up(N, _lib.CBO_NPAD)
+                b["x_obs_int"] = self._dev((d * N,))
+                b["x_obs_cond"] = self._dev((max(c * N, 1),))
+                b["mc_cond"] = self._dev((max(c * Smc, 1),))
+                b["alpha_obs"] = self._dev((N,))
+                b["kyinv"] = self._dev((N * N,))
+                for k in range(d):
+                    b[f"tab{k}"] = self._dev((len(pr.grid[k]) * Np,))
+                b["u_int"] = self._dev((self.ncap * Np,))
+                b["pbar"] = self._dev((Np,))
+                b["w"] = self._dev((Np,))
+                b["M"] = self._dev((Np * Np,))
+                b["m"] = self._dev((gc,))
+                b["v"] = self._dev((gc,))
+            self.buf.append(b)
+        # sweep scratch / outputs
+        self._fill_descs()
+        n_items = self.lib.cbo_sweep_num_items(self.h_sets, A) if A else 0
+        self.tile_best = torch.empty((max(n_items, 1) * C.sizeof(SetBest),), dtype=torch.uint8, device=self.device)
+        self.local_best = torch.empty((max(A, 1) * C.sizeof(SetBest),), dtype=torch.uint8, device=self.device)
+        self.result = torch.empty((C.sizeof(SweepResult),), dtype=torch.uint8, device=self.device)
+        S = len(self.problems)
+        self.global_best = torch.empty((S * C.sizeof(SetBest),), dtype=torch.uint8, device=self.device)
+        self.gathered = torch.empty((self.world * S * C.sizeof(SetBest),), dtype=torch.uint8, device=self.device)
+        empty = (SetBest * S)()
+        for s in range(S):
+            empty[s].value, empty[s].index = -np.inf, -1
+        self._empty_best = torch.frombuffer(bytearray(bytes(empty)), dtype=torch.uint8).to(self.device)
+
+    def _fill_descs(self):
+        for li, g in enumerate(self.active):
+            pr, b, D = self.problems[g], self.buf[li], self.h_sets[li]
+            d, n = pr.d, pr.x_int.shape[0]
+            gb, gc = self.slices[g]
+            D.d, D.n_int, D.causal = d, n, int(pr.causal)
+            for k in range(_lib.CBO_MAX_D):
+                D.p[k] = len(pr.grid[k]) if k < d else 1
+            D.g_total, D.g_begin, D.g_count = pr.g_total, gb, gc
+            D.cost_fix, D.cost_variable = float(pr.cost_fix), int(bool(pr.cost_variable))
+            ptr = lambda name: b[name].data_ptr() if name in b else None
+            for k in range(d):
+                D.grid[k] = ptr(f"grid{k}")
+            D.x_int, D.y_int, D.L, D.alpha = ptr("x_int"), ptr("y_int"), ptr("L"), ptr("alpha")
+            D.sqrt_v_int, D.m_int, D.v_int, D.fit_info = ptr("sqrt_v_int"), ptr("m_int"), ptr("v_int"), ptr("fit_info")
+            D.mu, D.var, D.ei, D.acq = ptr("mu"), ptr("var"), ptr("ei"), ptr("acq")
+            if pr.causal:
+                N, c, Smc = pr.x_obs_int.shape[0], pr.x_obs_cond.shape[1], pr.mc_cond.shape[0]
+                D.c, D.n_obs, D.n_obs_pad = c, N, _round_up(N, _lib.CBO_NPAD)
+                D.n_mc, D.n_mc_pad = Smc, _round_up(max(Smc, 1), _lib.CBO_SPAD)
+                D.s2, D.noise = float(pr.s2), float(pr.noise)
+                ls_int = np.broadcast_to(np.asarray(pr.ls_int, np.float64).reshape(-1), (d,)) if np.size(pr.ls_int) in (1, d) else None
+                if ls_int is None:
+                    raise ValueError(f"set {g}: ls_int must have 1 or d entries")
+                ls_cond = np.asarray(pr.ls_cond, np.float64).reshape(-1)
+                if c and ls_cond.size == 1:
+                    ls_cond = np.repeat(ls_cond, c)
+                if ls_cond.size != c:
+                    raise ValueError(f"set {g}: ls_cond must have c={c} entries")
+                for k in range(d):
+                    D.ls_int[k] = float(ls_int[k])
+                for k in range(c):
+                    D.ls_cond[k] = float(ls_cond[k])
+                D.x_obs_int, D.x_obs_cond, D.mc_cond = ptr("x_obs_int"), ptr("x_obs_cond"), ptr("mc_cond")
+                D.alpha_obs, D.kyinv = ptr("alpha_obs"), ptr("kyinv")
+                for k in range(d):
+                    D.tab[k] = ptr(f"tab{k}")
+                D.u_int, D.pbar, D.w, D.M = ptr("u_int"), ptr("pbar"), ptr("w"), ptr("M")
+                D.P = self.P.data_ptr() if (self.P is not None and c > 0) else None
+                D.m, D.v = ptr("m"), ptr("v")
+        A = len(self.active)
+        raw = bytearray(bytes(self.h_sets)) if A else bytearray(C.sizeof(SetDesc))
+        self.d_sets = torch.frombuffer(raw, dtype=torch.uint8).to(self.device)
+
+    # ------------------------------------------------------------------------------------------------
+    def _h2d(self, dst: torch.Tensor, arr: np.ndarray, key):
+        arr = np.ascontiguousarray(arr, dtype=np.float64).reshape(-1)
+        if arr.size == 0:
+            return 0
+        if self.pinned_staging:
+            st = self._pins.get(key)
+            if st is None or st.numel() != arr.size:
+                st = torch.empty((arr.size,), dtype=torch.float64).pin_memory()
+                self._pins[key] = st
+            st.numpy()[:] = arr
+            dst[:arr.size].copy_(st, non_blocking=True)
+        else:
+            dst[:arr.size].copy_(torch.from_numpy(arr))
+        return arr.nbytes
+
+    def upload(self, what: str = "all") -> int:
+        """Copy the host inputs to the device (returns bytes moved).  what = 'all' | 'interventional'."""
+        if not hasattr(self, "_pins"):
+            self._pins: Dict[object, torch.Tensor] = {}
+        total = 0
+        for li, g in enumerate(self.active):
+            pr, b = self.problems[g], self.buf[li]
+            total += self._h2d(b["x_int"], pr.x_int, (li, "x_int"))
+            total += self._h2d(b["y_int"], pr.y_int, (li, "y_int"))
+            if what == "interventional":
+                continue
+            for k in range(pr.d):
+                total += self._h2d(b[f"grid{k}"], pr.grid[k], (li, f"grid{k}"))
+            if pr.causal:
+                total += self._h2d(b["x_obs_int"], np.asarray(pr.x_obs_int).T, (li, "x_obs_int"))
+                total += self._h2d(b["x_obs_cond"], np.asarray(pr.x_obs_cond).T, (li, "x_obs_cond"))
+                total += self._h2d(b["mc_cond"], np.asarray(pr.mc_cond).T, (li, "mc_cond"))
+                total += self._h2d(b["alpha_obs"], pr.alpha_obs, (li, "alpha_obs"))
+                total += self._h2d(b["kyinv"], pr.kyinv, (li, "kyinv"))
+        return total
+
+    def set_interventional(self, g: int, x_int: np.ndarray, y_int: np.ndarray):
+        """Replace the interventional data of global set g (Monitor.add_intervention_data, Monitor.py:148-160)."""
+        pr = self.problems[g]
+        pr.x_int = np.asarray(x_int, np.float64).reshape(-1, pr.d)
+        pr.y_int = np.asarray(y_int, np.float64).reshape(-1)
+        if pr.x_int.shape[0] > self.ncap:
+            raise ValueError(f"set {g}: n_int={pr.x_int.shape[0]} exceeds capacity {self.ncap}")
+        if g in self.local_of:
+            li = self.local_of[g]
+            self.h_sets[li].n_int = pr.x_int.shape[0]
+            self._h2d(self.buf[li]["x_int"], pr.x_int, (li, "x_int"))
+            self._h2d(self.buf[li]["y_int"], pr.y_int, (li, "y_int"))
+            off = li * C.sizeof(SetDesc)
+            raw = bytearray(bytes(self.h_sets[li]))
+            self.d_sets[off:off + len(raw)].copy_(torch.frombuffer(raw, dtype=torch.uint8))
+
+    # ------------------------------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _subset(self, local_ids: Optional[Sequence[int]]):
+        """(host descriptor pointer, device descriptor pointer, count) for all active sets or a contiguous run."""
+        A = len(self.active)
+        if local_ids is None:
+            return self.h_sets, C.c_void_p(self.d_sets.data_ptr()), A
+        ids = list(local_ids)
+        if ids != list(range(ids[0], ids[0] + len(ids))):
+            raise ValueError("subset must be a contiguous run of local set ids")
+        h = C.cast(C.byref(self.h_sets, ids[0] * C.sizeof(SetDesc)), C.POINTER(SetDesc))
+        return h, C.c_void_p(self.d_sets.data_ptr() + ids[0] * C.sizeof(SetDesc)), len(ids)
+
+    def _timed(self, name, fn, out):
+        if not self.timing:
+            fn()
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream(self.device))
+        fn()
+        e1.record(torch.cuda.current_stream(self.device))
+        out.append((name, e0, e1))
+
+    def build_tables(self, local_ids=None):
+        h, _, n = self._subset(local_ids)
+        if n:
+            _lib.check(self.lib.cbo_build_tables(h, n, self._stream()), "cbo_build_tables")
+
+    def prior_precompute(self, local_ids=None):
+        h, _, n = self._subset(local_ids)
+        if n:
+            _lib.check(self.lib.cbo_prior_precompute(h, n, self._stream()), "cbo_prior_precompute")
+
+    def prior_eval(self, which: int, local_ids=None):
+        h, dptr, n = self._subset(local_ids)
+        if n:
+            _lib.check(self.lib.cbo_prior_eval(h, dptr, n, which, self._stream()), "cbo_prior_eval")
+
+    def posterior_fit(self, local_ids=None):
+        h, dptr, n = self._subset(local_ids)
+        if n:
+            _lib.check(self.lib.cbo_posterior_fit(h, dptr, n, self._stream()), "cbo_posterior_fit")
+
+    def _sweep_local(self, best: float, task: str):
+        A = len(self.active)
+        if task not in ("min", "max"):
+            raise ValueError("task must be 'min' or 'max'")
+        if A:
+            _lib.check(self.lib.cbo_sweep(self.h_sets, C.c_void_p(self.d_sets.data_ptr()), A, float(best),
+                                          1 if task == "min" else -1, C.c_void_p(self.tile_best.data_ptr()),
+                                          C.c_void_p(self.local_best.data_ptr()), C.c_void_p(self.result.data_ptr()),
+                                          self._stream()), "cbo_sweep")
+
+    def _finish(self, events) -> SweepOutput:
+        """Scatter the local per-set bests into the global table, all-gather over ranks (NCCL), combine on
+        the device with the same deterministic rule on every rank, and read the 24-byte result back."""
+        S, sb = len(self.problems), C.sizeof(SetBest)
+        gb = self.global_best
+        gb.copy_(self._empty_best)
+        gv, lv = gb.view(S, sb), self.local_best.view(-1, sb)
+        if self.active:
+            idx = torch.as_tensor(self.active, device=self.device, dtype=torch.long)
+            gv.index_copy_(0, idx, lv[:len(self.active)])
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self.gathered, gb, group=self.group)
+            src, nr = self.gathered, self.world
+        else:
+            src, nr = gb, 1
+        _lib.check(self.lib.cbo_argmax_combine(C.c_void_p(src.data_ptr()), nr, S, C.c_void_p(gb.data_ptr()),
+                                               C.c_void_p(self.result.data_ptr()), self._stream()), "cbo_argmax_combine")
+        res_h = self.result.cpu().numpy().tobytes()      # device -> host read of the step's result (synchronises)
+        best_h = gb.cpu().numpy().tobytes()
+        r = SweepResult.from_buffer_copy(res_h)
+        bests = (SetBest * S).from_buffer_copy(best_h)
+        x = None
+        if r.set >= 0:
+            pr = self.problems[r.set]
+            ii = np.unravel_index(r.index, [len(t) for t in pr.grid])
+            x = np.array([pr.grid[k][ii[k]] for k in range(pr.d)])
+        ms = {}
+        for name, e0, e1 in events:
+            ms[name] = ms.get(name, 0.0) + e0.elapsed_time(e1)
+        return SweepOutput(r.set, r.index, r.value, x, np.array([b.value for b in bests]),
+                           np.array([b.index for b in bests], dtype=np.int64), r.n_nan, ms)
+
+    def sweep(self, best: float, task: str = "min") -> SweepOutput:
+        """Full post-observation trial: prior precompute + prior on x_int and on the grid + posterior fit +
+        EI / cost + argmax (reference CBO.intervene after an observe(), CBO.py:143-173)."""
+        ev: list = []
+        self._timed("tables", self.build_tables, ev)
+        self._timed("prior_precompute", self.prior_precompute, ev)
+        self._timed("prior_eval_train", lambda: self.prior_eval(1), ev)
+        self._timed("posterior_fit", self.posterior_fit, ev)
+        self._timed("prior_eval_grid", lambda: self.prior_eval(0), ev)
+        self._timed("sweep", lambda: self._sweep_local(best, task), ev)
+        return self._finish(ev)
+
+    def refresh(self, best: float, task: str = "min", refit: Sequence[int] = ()) -> SweepOutput:
+        """Post-intervention trial: the prior on the grid is cached; only the sets in `refit` (global ids) get
+        their interventional table, prior at x_int and posterior refreshed
+        (CBO.update_gaussian_process_of_last_intervention, CBO.py:224-235), then EI everywhere."""
+        ev: list = []
+        for g in refit:
+            if g not in self.local_of:
+                continue
+            li = [self.local_of[g]]
+            if self.problems[g].causal:
+                self._timed("tables", lambda: self.build_tables(li), ev)
+                self._timed("prior_eval_train", lambda: self.prior_eval(1, li), ev)
+            self._timed("posterior_fit", lambda: self.posterior_fit(li), ev)
+        self._timed("sweep", lambda: self._sweep_local(best, task), ev)
+        return self._finish(ev)
+
+    # ------------------------------------------------------------------------------------------------
+    def fetch(self, name: str, g: int) -> np.ndarray:
+        """Device array of global set g as NumPy (parity tests / debugging)."""
+        li = self.local_of[g]
+        pr, b, D = self.problems[g], self.buf[li], self.h_sets[li]
+        t = b[name].cpu().numpy()
+        n = D.n_int
+        if name in ("m", "v", "mu", "var", "ei", "acq"):
+            return t[:D.g_count]
+        if name == "L":
+            return t[:n * n].reshape(n, n)
+        if name in ("alpha", "sqrt_v_int", "m_int", "v_int", "y_int"):
+            return t[:n]
+        if name == "x_int":
+            return t[:n * pr.d].reshape(n, pr.d)
+        if name == "M":
+            return t.reshape(D.n_obs_pad, D.n_obs_pad)[:D.n_obs, :D.n_obs]
+        if name in ("w", "pbar"):
+            return t[:D.n_obs]
+        if name == "u_int":
+            return t[:n * D.n_obs_pad].reshape(n, D.n_obs_pad)[:, :D.n_obs]
+        if name.startswith("tab"):
+            k = int(name[3:])
+            return t.reshape(D.p[k], D.n_obs_pad)[:, :D.n_obs]
+        return t

@@ -1,0 +1,165 @@
+/* cbo_b200.h -- C ABI of libcbo_b200.so: the B200-native (sm_100a) per-trial acquisition sweep of
+ * Causal Bayesian Optimisation (causal prior -> per-set GP posterior -> EI / cost -> argmax).
+ *
+ * The reference (ChampiB/CBO_with_OOP) is pure Python and has no FFI; each entry point below names the
+ * reference call site whose arithmetic it replaces (paths relative to the reference checkout).  The
+ * reference-side binding a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - every pointer inside cbo_set_desc is a CUDA DEVICE pointer to float64 unless stated otherwise;
+ *    the caller owns every allocation (PyTorch tensors in the shipped host code), the library allocates
+ *    nothing and keeps no global state besides a thread-local error string;
+ *  - `h_sets` is a HOST array of descriptors, `d_sets` the same bytes resident on the device;
+ *  - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it and re-entrant per stream;
+ *  - return value: 0 ok, <0 invalid argument (see cbo_last_error), >0 a cudaError_t;
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point returns an error.
+ */
+#ifndef CBO_B200_H
+#define CBO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CBO_API __attribute__((visibility("default")))
+#else
+#define CBO_API
+#endif
+
+#define CBO_ABI_VERSION 1
+#define CBO_MAX_D 4          /* intervened dimensions per exploration set (reference uses 1..3) */
+#define CBO_MAX_C 8          /* conditioning dimensions of an observational GP */
+#define CBO_MAX_NINT 128     /* interventional rows per set (reference: 10 .. ~50) */
+#define CBO_NPAD 128         /* n_obs_pad must be a multiple of this */
+#define CBO_SPAD 16          /* n_mc_pad must be a multiple of this */
+#define CBO_PRIOR_TILE 128   /* grid points per prior-eval work item */
+#define CBO_SWEEP_TILE 128   /* grid points per sweep work item (one thread each) */
+
+/* One exploration set.  Index conventions follow SURVEY.md §8(d): the candidate grid is the tensor
+ * product of per-dimension coordinate tables, flattened C-order (last dimension fastest). */
+typedef struct cbo_set_desc {
+    /* ---- sizes ------------------------------------------------------------------------------- */
+    int32_t d;            /* intervened dims */
+    int32_t c;            /* conditioning dims */
+    int32_t n_obs;        /* N: training rows of the observational GP */
+    int32_t n_obs_pad;    /* leading dimension of tab/u_int/M/w/pbar/P rows; multiple of CBO_NPAD */
+    int32_t n_mc;         /* S_mc: conditioning samples averaged over (reference: = n_obs) */
+    int32_t n_mc_pad;     /* leading dimension of P; multiple of CBO_SPAD */
+    int32_t n_int;        /* n: interventional rows */
+    int32_t causal;       /* 1: causal prior mean + CausalRBF; 0: zero mean + RBF (NON_CAUSAL_GP) */
+    int32_t p[CBO_MAX_D]; /* grid points per intervened dim */
+    int64_t g_total;      /* prod p[k] */
+    int64_t g_begin;      /* this rank evaluates flat grid indices [g_begin, g_begin + g_count) */
+    int64_t g_count;
+    /* ---- observational GP: inputs (utils.py:40-45 fit, hyper-parameters frozen) ---------------- */
+    const double* x_obs_int;   /* (d, n_obs)   intervened columns of the training design, one row per dim */
+    const double* x_obs_cond;  /* (c, n_obs)   conditioning columns of the training design */
+    const double* mc_cond;     /* (c, n_mc)    conditioning samples (DoCalculus.py:85-88 non-intervened columns) */
+    const double* alpha_obs;   /* (n_obs)      Ky^-1 y */
+    const double* kyinv;       /* (n_obs, n_obs) row-major, Ky^-1 */
+    double ls_int[CBO_MAX_D];  /* lengthscale per intervened dim */
+    double ls_cond[CBO_MAX_C]; /* lengthscale per conditioning dim */
+    double s2;                 /* RBF variance */
+    double noise;              /* likelihood variance (1e-2, utils.py:43) */
+    /* ---- causal prior: work buffers written by the library --------------------------------------- */
+    double* tab[CBO_MAX_D];    /* (p[k], n_obs_pad) exp tables, zero for j >= n_obs */
+    double* u_int;             /* (n_int, n_obs_pad) exp table of the interventional rows */
+    double* P;                 /* (n_obs_pad, n_mc_pad) scratch; may be shared between sets (stream-ordered) */
+    double* pbar;              /* (n_obs_pad) */
+    double* w;                 /* (n_obs_pad) s2 * alpha * pbar, zero padded */
+    double* M;                 /* (n_obs_pad, n_obs_pad) s2^2 Kyinv o (P P^T / S_mc), symmetric, zero padded */
+    /* ---- interventional data and the per-set GP ------------------------------------------------ */
+    const double* grid[CBO_MAX_D]; /* (p[k]) candidate coordinates per dim (np.linspace tables from the host) */
+    const double* x_int;       /* (n_int, d) row-major */
+    const double* y_int;       /* (n_int) */
+    double* m_int;             /* (n_int) prior mean at x_int      [written by cbo_prior_eval which=1] */
+    double* v_int;             /* (n_int) prior variance at x_int  */
+    double* L;                 /* (n_int, n_int) row-major lower Cholesky factor [cbo_posterior_fit] */
+    double* alpha;             /* (n_int) Ky^-1 (y - m) */
+    double* sqrt_v_int;        /* (n_int) sqrt(v_int) */
+    int32_t* fit_info;         /* [0] jitter retries used (0..5), [1] 0 ok / 1 not positive definite */
+    /* ---- acquisition ----------------------------------------------------------------------------- */
+    double cost_fix;           /* sum of the fixed costs of the set's variables (cost_functions.py:11-17) */
+    int32_t cost_variable;     /* 1: add sum_k |x_k| per candidate (GraphInterface.py:46-50) */
+    int32_t reserved0;
+    /* ---- per-candidate arrays, indexed by (g - g_begin) ----------------------------------------- */
+    double* m;                 /* (g_count) prior mean       [cbo_prior_eval which=0]; required when causal */
+    double* v;                 /* (g_count) prior variance */
+    double* mu;                /* optional (may be NULL): posterior mean */
+    double* var;               /* optional: posterior variance incl. 1e-10 noise */
+    double* ei;                /* optional: expected improvement */
+    double* acq;               /* optional: ei / cost */
+} cbo_set_desc;
+
+/* Result of one sweep on one rank. */
+typedef struct cbo_set_best {
+    double value;     /* max acquisition over the rank's slice of the set; -inf when the slice is empty */
+    int64_t index;    /* flat grid index of the first maximiser; -1 when empty */
+    int32_t n_nan;    /* candidates of the slice whose acquisition was NaN */
+    int32_t reserved;
+} cbo_set_best;
+
+typedef struct cbo_sweep_result {
+    double value;      /* best acquisition over all sets (ties: lowest set, then lowest index; NaN = -inf) */
+    int64_t index;     /* flat grid index inside the set */
+    int32_t set;       /* exploration-set index; -1 when nothing was evaluated */
+    int32_t n_nan;     /* candidates whose acquisition was NaN (negative predictive variance) */
+} cbo_sweep_result;
+
+CBO_API int cbo_abi_version(void);
+CBO_API size_t cbo_sizeof_set_desc(void);
+/* Offset of a named field of cbo_set_desc, or -1: lets a foreign-language binding verify its mirror. */
+CBO_API long cbo_offsetof_set_desc(const char* field);
+CBO_API const char* cbo_last_error(void);
+
+/* Number of sweep work items (tiles of CBO_SWEEP_TILE candidates) for this descriptor list; host-side
+ * arithmetic only.  Callers size `d_tile_best` with it. */
+CBO_API long cbo_sweep_num_items(const cbo_set_desc* h_sets, int num_sets);
+
+/* K0. exp tables: tab[k][i][j] = exp(-.5 ((grid[k][i] - x_obs_int[k][j]) / ls_int[k])^2) and
+ * u_int[i][j] = exp(-.5 sum_k ((x_int[i][k] - x_obs_int[k][j]) / ls_int[k])^2).
+ * Replaces the kernel evaluations inside gp.predict at DoCalculus.py:77 for the intervened columns. */
+CBO_API int cbo_build_tables(const cbo_set_desc* h_sets, int num_sets, void* stream);
+
+/* K1a. P, pbar, w, M from the observational GP state and the conditioning samples.
+ * Replaces the per-candidate np.hstack + gp.predict set-up of DoCalculus.py:68-89 (done once per
+ * observation instead of once per candidate). */
+CBO_API int cbo_prior_precompute(const cbo_set_desc* h_sets, int num_sets, void* stream);
+
+/* K1b. causal prior m(x) = u.w, v(x) = s2 + noise - u^T M u.
+ * which = 0: on the rank's slice of the tensor grid (writes m, v);
+ * which = 1: on the interventional rows x_int (writes m_int, v_int).
+ * Replaces DoCalculus.update_do_function (DoCalculus.py:34-66), index 0 and 1 together. */
+CBO_API int cbo_prior_eval(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_sets, int which, void* stream);
+
+/* K2. one CTA per set: Gram of the interventional rows (CausalRBF.K, causal_kernels.py:45-62, or RBF),
+ * + (1e-10 + 1e-8) I, Cholesky with GPy's jitter-retry rule, alpha = Ky^-1 (y - m).
+ * Replaces GPRegression(...) at GaussianProcessFactory.py:57-73 (GPy ExactGaussianInference). */
+CBO_API int cbo_posterior_fit(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_sets, void* stream);
+
+/* K3 + K4. per candidate: k*, mu, forward substitution, var, EI, / cost; per-tile first-argmax; then a
+ * deterministic reduction to per-set bests and the global best.
+ * Replaces model.predict + CausalExpectedImprovement.evaluate + Cost.evaluate + the anchor top-1
+ * (causal_acquisition_functions.py:27-43, utils.py:29-37, causal_optimizer.py:52-55) and
+ * CBO.select_next_intervention (CBO.py:269-277).
+ * task_sign: +1 for task 'min', -1 for 'max' (causal_acquisition_functions.py:38-41).
+ * d_tile_best: device scratch of cbo_sweep_num_items() cbo_set_best entries; outputs: d_set_best
+ * (num_sets entries), d_result (1 entry). */
+CBO_API int cbo_sweep(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_sets, double best,
+              int task_sign, cbo_set_best* d_tile_best, cbo_set_best* d_set_best,
+              cbo_sweep_result* d_result, void* stream);
+
+/* K4 (multi-GPU). Combine `num_ranks` gathered per-set bests (rank-major: [rank][set]) into the global
+ * per-set bests and the global result with the same rule on every rank.  Runs on the device so the
+ * all-gathered buffer never leaves it. */
+CBO_API int cbo_argmax_combine(const cbo_set_best* d_gathered, int num_ranks, int num_sets,
+                       cbo_set_best* d_set_best, cbo_sweep_result* d_result, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CBO_B200_H */

@@ -1,0 +1,53 @@
+"""Shared builders for the parity tests: a seeded random exploration-set problem, its oracle evaluation
+(oracle/cbo_oracle.py -- the checker, never the thing under test) and the tolerance rules."""
+from __future__ import annotations
+
+import numpy as np
+
+from oracle import cbo_oracle as O
+
+
+def make_case(seed, N=96, d=2, c=2, n=9, p=(7, 11), S_mc=None, ard=True, causal=True, cost_variable=False,
+              lo=-2.0, hi=2.0, duplicate_train_point=False):
+    """Returns (problem kwargs for SetProblem, oracle inputs dict)."""
+    rng = np.random.default_rng(seed)
+    D = d + c
+    X = rng.standard_normal((N, D))
+    a = rng.uniform(-1, 1, D)
+    y = np.sin(X @ a) + 0.1 * rng.standard_normal(N)
+    s2 = float(rng.uniform(0.6, 1.6))
+    ls = rng.uniform(0.7, 1.8, D) if ard else np.array([float(rng.uniform(0.8, 1.5))])
+    gp = O.obs_gp_fit(X, y, s2, ls, form="diff")
+    ls_full = ls if ard else np.repeat(ls, D)
+    cond = X if S_mc is None else rng.standard_normal((S_mc, D))
+    grid = [np.linspace(lo, hi, p[k]) for k in range(d)]
+    x_int = rng.uniform(lo, hi, (n, d))
+    if duplicate_train_point:  # a candidate that coincides with an interventional row: variance ~ 1e-8
+        x_int[0] = [grid[k][p[k] // 2] for k in range(d)]
+    y_int = np.sin(x_int @ a[:d]) + 0.05 * rng.standard_normal(n)
+    kw = dict(x_obs_int=X[:, :d].copy(), x_obs_cond=X[:, d:].copy(), mc_cond=cond[:, d:].copy(), alpha_obs=gp["alpha"],
+              kyinv=gp["Kyinv"], ls_int=ls_full[:d].copy(), ls_cond=ls_full[d:].copy(), s2=s2, grid=grid, x_int=x_int,
+              y_int=y_int, cost_fix=float(d), cost_variable=cost_variable, causal=causal, name=f"case{seed}")
+    ora = dict(gp=gp, cond=cond, cols=list(range(d)), XI=x_int, yI=y_int, tables=grid, fix=np.ones(d),
+               variable=cost_variable, causal=causal)
+    return kw, ora
+
+
+def oracle_sweep(ora, best, task="min", form="diff", prior="factorised"):
+    return O.sweep_set(ora["gp"], ora["cond"], ora["cols"], ora["XI"], ora["yI"], ora["tables"], best, task,
+                       fix_costs=ora["fix"], variable_cost=ora["variable"], causal=ora["causal"], prior=prior, form=form)
+
+
+# ---- tolerance (north_star: 1e-6 relative in fp64; SURVEY.md §7 "parity definition near zero variance") ----
+RTOL = 1e-6
+
+
+def rel_err(got, ref, floor):
+    """|got-ref| / max(|ref|, floor), elementwise; the floor ties 'relative' to the scale of the quantity where
+    the reference value itself is a difference of O(1) terms."""
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    return np.abs(got - ref) / np.maximum(np.abs(ref), floor)
+
+
+def floor_count(ref, floor):
+    return int(np.sum(np.abs(np.asarray(ref)) < floor))
