@@ -15,15 +15,30 @@ constexpr int kBK = 16;  // k depth of one pipeline stage
 
 __device__ __forceinline__ int frag_off(int rows, int kb, int r, int kk) { return ((kb * rows + r) << 2) + kk; }
 
+// Blocked global layout of the prior matrix M (written by K1a, streamed by K1b): the 128-row x 16-column slab
+// (row block jb, k block kt) is stored contiguously and already in fragment order, so one pipeline stage of
+// K1b is a single contiguous 16 KB TMA bulk copy.  Element (n, k) of the Npad x Npad matrix:
+constexpr int kMBlkRows = 128;
+constexpr int kMBlkDoubles = kMBlkRows * kBK;
+__host__ __device__ __forceinline__ size_t mblk_base(int jb, int kt, int npad) {
+    return ((size_t)jb * (npad / kBK) + kt) * kMBlkDoubles;
+}
+__host__ __device__ __forceinline__ size_t mblk_off(int n, int k, int npad) {
+    return mblk_base(n / kMBlkRows, k / kBK, npad) + ((((k % kBK) >> 2) * kMBlkRows + (n % kMBlkRows)) << 2) + (k & 3);
+}
+
 // Asynchronously copy ROWS x 16 doubles (global row pitch `ld`, 16-byte aligned) into a fragment-order slab.
 template <int ROWS, int NT>
 __device__ __forceinline__ void load_rows_async(double* slab, const double* __restrict__ g, size_t ld, int tid) {
     constexpr int CH = kBK / 2;  // 16-byte chunks per row
     static_assert((ROWS * CH) % NT == 0, "slab must divide evenly over the CTA");
 #pragma unroll
+    // 128-bit shared accesses are served per quarter-warp: 8 consecutive lanes take the same k4-group of four
+    // consecutive rows (128 contiguous bytes of the slab -> all 32 banks), the warp still reads 4 full 128-byte lines.
     for (int it = 0; it < ROWS * CH / NT; ++it) {
         const int idx = tid + it * NT;
-        const int r = idx / CH, ch = idx % CH;
+        const int l = idx & 31;
+        const int r = (idx >> 5) * 4 + ((l & 7) >> 1), ch = (l >> 3) * 2 + (l & 1);
         cp_async16(slab + frag_off(ROWS, ch >> 1, r, (ch & 1) * 2), g + (size_t)r * ld + ch * 2);
     }
 }

@@ -10,10 +10,12 @@
 // doubled, and the (full, symmetric) diagonal block is added.  One CTA owns 128 candidates.
 //
 // Warp-specialised, mbarrier-synchronised pipeline (one CTA per SM, persistent over its k loop):
-//   producer warps (4)  : per stage, stream a BN x 16 slab of M with cp.async (completion signalled on the stage's
-//                         "full" mbarrier) and REGENERATE the 128 x 16 slab of U from the L2-resident exp tables
-//                         (d loads + (d-1) multiplies per element, written in DMMA fragment order);
-//                         all global-load latency is absorbed here;
+//   producer warps (4)  : per stage, one thread issues a single 16 KB TMA bulk copy (cp.async.bulk, SASS UBLKCP) of
+//                         the M slab -- K1a stores M blocked in fragment order, so the slab is contiguous -- whose
+//                         bytes complete on the stage's "full" mbarrier; all producer threads REGENERATE the
+//                         128 x 16 slab of U from the L2-resident exp tables (d loads + (d-1) multiplies per
+//                         element, conflict-free STS.128 in DMMA fragment order); all global-load latency is
+//                         absorbed here;
 //   consumer warps (8)  : wait "full", 4 x (12 LDS.64 + 32 DMMA.8x8x4), arrive on "empty"; they never touch
 //                         global memory inside the k loop, so the FP64 tensor pipe is the only thing they wait for.
 // Registers are re-balanced with setmaxnreg (producers shrink, consumers hold the 128 x 128 accumulator tile).
@@ -46,7 +48,8 @@ struct PriorCfg {
     static_assert(BM == CBO_PRIOR_TILE, "host item count assumes CBO_PRIOR_TILE points per CTA");
     static_assert(PW % 4 == 0 && (WM * WN) % 4 == 0, "setmaxnreg works on whole warpgroups");
     static_assert(BM % ROWS_PER_PASS == 0 && PASSES % PASS_GROUP == 0, "U generation mapping");
-    static_assert(CBO_NPAD % BN == 0, "n_obs_pad must be a whole number of J blocks");
+    static_assert(BN == kMBlkRows, "the J block must match the row block of M's blocked layout");
+    static_assert(NPROD == 128, "producer lane mapping assumes 4 warps x 4 rows per pass");
 };
 
 template <class Cfg, int D, int PROD_REGS, int CONS_REGS>
@@ -122,7 +125,7 @@ prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, int which
     for (int i = tid; i < 2 * WN * BM; i += Cfg::NT) sRed[i] = 0.0;
     if (tid == 0) {
         for (int i = 0; i < STAGES; ++i) {
-            mbar_init(&full[i], 2 * NPROD);       // per producer thread: one cp.async-completion arrive + one explicit arrive
+            mbar_init(&full[i], NPROD + 1);        // every producer thread after its U rows + the expect_tx arrive of the TMA issuer
             mbar_init(&empty[i], Cfg::WM * WN);  // one arrive per consumer warp
         }
         mbar_fence_init();
@@ -132,38 +135,52 @@ prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, int which
     if (warp < Cfg::PW) {
         // =============================== PRODUCER ===============================
         setmaxnreg_dec<PROD_REGS>();
-        const int kpair = tid & 7, prow0 = tid >> 3;
+        // lane -> (k4 group, row, half): a quarter-warp writes 128 contiguous bytes of the slab (conflict-free
+        // STS.128) and the warp reads four full 128-byte table lines per load instruction
+        const int pkb = lane >> 3, phalf = lane & 1;
+        const int prow0 = warp * 4 + ((lane & 7) >> 1);
+        const int jlane = pkb * 4 + phalf * 2;
+        constexpr int PG = Cfg::PASS_GROUP;
+        double2 t[PG][D];
+        auto issue_loads = [&](int g0, int kt) {  // every load of the group is issued before the first use
+            const int j = kt * kBK + jlane;
+#pragma unroll
+            for (int q = 0; q < PG; ++q) {
+                const int row = prow0 + (g0 + q) * Cfg::ROWS_PER_PASS;
+#pragma unroll
+                for (int k = 0; k < D; ++k) t[q][k] = ldg_nc_d2(tab[k] + sRow[k * BM + row] + j);
+            }
+        };
+        auto finish_group = [&](int g0, double* slab) {
+#pragma unroll
+            for (int q = 0; q < PG; ++q) {
+                const int row = prow0 + (g0 + q) * Cfg::ROWS_PER_PASS;
+                const double live = (double)sRow[D * BM + row];
+                double2 v = make_double2(t[q][0].x * live, t[q][0].y * live);
+#pragma unroll
+                for (int k = 1; k < D; ++k) { v.x *= t[q][k].x; v.y *= t[q][k].y; }
+                *reinterpret_cast<double2*>(slab + frag_off(BM, pkb, row, phalf * 2)) = v;
+            }
+        };
         int stage = 0;
         unsigned phase = 0;
 #pragma unroll 1
         for (int jb = 0; jb < nJ; ++jb) {
             const int nk = (jb + 1) * KB_PER_J;
-            const double* __restrict__ Mj = M + (size_t)jb * BN * Npad;
 #pragma unroll 1
             for (int kt = 0; kt < nk; ++kt) {
+                issue_loads(0, kt);                       // table loads do not need the smem slot: start them first
                 mbar_wait(&empty[stage], phase ^ 1u);
-                load_rows_async<BN, NPROD>(sB + stage * Cfg::B_TILE, Mj + (size_t)kt * kBK, Npad, tid);
-                cp_async_mbar_arrive_noinc(&full[stage]);
+                if (tid == 0) {                           // M slab: one contiguous 16 KB TMA bulk copy
+                    mbar_arrive_expect_tx(&full[stage], Cfg::B_TILE * sizeof(double));
+                    bulk_g2s(sB + stage * Cfg::B_TILE, M + mblk_base(jb, kt, Npad), Cfg::B_TILE * sizeof(double), &full[stage]);
+                }
                 double* slab = sA + stage * Cfg::A_TILE;
-                const int j = kt * kBK + 2 * kpair;
+                finish_group(0, slab);
 #pragma unroll
-                for (int g0 = 0; g0 < Cfg::PASSES; g0 += Cfg::PASS_GROUP) {
-                    double2 t[Cfg::PASS_GROUP][D];  // every load of the group is issued before the first use
-#pragma unroll
-                    for (int q = 0; q < Cfg::PASS_GROUP; ++q) {
-                        const int row = prow0 + (g0 + q) * Cfg::ROWS_PER_PASS;
-#pragma unroll
-                        for (int k = 0; k < D; ++k) t[q][k] = ldg_nc_d2(tab[k] + sRow[k * BM + row] + j);
-                    }
-#pragma unroll
-                    for (int q = 0; q < Cfg::PASS_GROUP; ++q) {
-                        const int row = prow0 + (g0 + q) * Cfg::ROWS_PER_PASS;
-                        const double live = (double)sRow[D * BM + row];
-                        double2 v = make_double2(t[q][0].x * live, t[q][0].y * live);
-#pragma unroll
-                        for (int k = 1; k < D; ++k) { v.x *= t[q][k].x; v.y *= t[q][k].y; }
-                        *reinterpret_cast<double2*>(slab + frag_off(BM, kpair >> 1, row, (kpair & 1) * 2)) = v;
-                    }
+                for (int g0 = PG; g0 < Cfg::PASSES; g0 += PG) {
+                    issue_loads(g0, kt);
+                    finish_group(g0, slab);
                 }
                 mbar_arrive(&full[stage]);
                 if (++stage == STAGES) { stage = 0; phase ^= 1u; }

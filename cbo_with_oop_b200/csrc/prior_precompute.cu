@@ -8,7 +8,8 @@
 // so it is computed once here.  Two kernels per set, stream-ordered:
 //   pgen : P (N x S) with one exp per element, coalesced along i, deterministic row sums -> pbar, w
 //   syrk : lower block triangle of P P^T on the FP64 tensor pipe (DMMA), fused Hadamard with Kyinv,
-//          mirrored store so M is a full symmetric matrix.
+//          mirrored store so M is a full symmetric matrix, written in the blocked fragment-order layout of
+//          dmma_tile.cuh (mblk_off) that K1b streams with one TMA bulk copy per pipeline stage.
 // Roofline: FP64 pipe, 2 N^2 S_mc dense-counted flops (N^2 S_mc executed).  No conditioning columns (c == 0)
 // degenerates to M = s2^2 Kyinv.
 #include "dmma_tile.cuh"
@@ -67,7 +68,7 @@ nocond_kernel(const double* __restrict__ kyinv, const double* __restrict__ alpha
     const int j = blockIdx.y;
     const bool lj = j < n_obs;
     for (int k = blockIdx.x * 256 + threadIdx.x; k < n_obs_pad; k += gridDim.x * 256) {
-        M[(size_t)j * n_obs_pad + k] = (lj && k < n_obs) ? (s2 * s2) * kyinv[(size_t)j * n_obs + k] : 0.0;
+        M[mblk_off(j, k, n_obs_pad)] = (lj && k < n_obs) ? (s2 * s2) * kyinv[(size_t)j * n_obs + k] : 0.0;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         pbar[j] = lj ? 1.0 : 0.0;
@@ -143,10 +144,10 @@ syrk_kernel(const double* __restrict__ P, int n_mc_pad, const double* __restrict
                 if (cidx < n_obs) v0 = coef * kyinv[(size_t)r * n_obs + cidx] * acc[mi][ni][0];
                 if (cidx + 1 < n_obs) v1 = coef * kyinv[(size_t)r * n_obs + cidx + 1] * acc[mi][ni][1];
             }
-            *reinterpret_cast<double2*>(M + (size_t)r * n_obs_pad + cidx) = make_double2(v0, v1);
+            *reinterpret_cast<double2*>(M + mblk_off(r, cidx, n_obs_pad)) = make_double2(v0, v1);
             if (bi != bj) {
-                M[(size_t)cidx * n_obs_pad + r] = v0;
-                M[(size_t)(cidx + 1) * n_obs_pad + r] = v1;
+                M[mblk_off(cidx, r, n_obs_pad)] = v0;
+                M[mblk_off(cidx + 1, r, n_obs_pad)] = v1;
             }
         }
     }

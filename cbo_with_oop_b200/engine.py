@@ -399,8 +399,9 @@ class SweepEngine:
             return t[:n]
         if name == "x_int":
             return t[:n * pr.d].reshape(n, pr.d)
-        if name == "M":
-            return t.reshape(D.n_obs_pad, D.n_obs_pad)[:D.n_obs, :D.n_obs]
+        if name == "M":   # stored blocked ([row block][k block][k4 group][row][4], see include/cbo_b200.h)
+            Np = D.n_obs_pad
+            return t.reshape(Np // 128, Np // 16, 4, 128, 4).transpose(0, 3, 1, 2, 4).reshape(Np, Np)[:D.n_obs, :D.n_obs]
         if name in ("w", "pbar"):
             return t[:D.n_obs]
         if name == "u_int":

@@ -71,7 +71,9 @@ typedef struct cbo_set_desc {
     double* P;                 /* (n_obs_pad, n_mc_pad) scratch; may be shared between sets (stream-ordered) */
     double* pbar;              /* (n_obs_pad) */
     double* w;                 /* (n_obs_pad) s2 * alpha * pbar, zero padded */
-    double* M;                 /* (n_obs_pad, n_obs_pad) s2^2 Kyinv o (P P^T / S_mc), symmetric, zero padded */
+    double* M;                 /* n_obs_pad^2 doubles: s2^2 Kyinv o (P P^T / S_mc), symmetric, zero padded, stored BLOCKED:
+                                  element (n,k) at ((n/128)*(n_obs_pad/16) + k/16)*2048 + (((k%16)/4)*128 + n%128)*4 + k%4,
+                                  i.e. every 128-row x 16-column slab is contiguous and in DMMA fragment order */
     /* ---- interventional data and the per-set GP ------------------------------------------------ */
     const double* grid[CBO_MAX_D]; /* (p[k]) candidate coordinates per dim (np.linspace tables from the host) */
     const double* x_int;       /* (n_int, d) row-major */
