@@ -49,6 +49,7 @@ class SweepResult(C.Structure):
 
 EXPORTS = [
     "cbo_abi_version", "cbo_sizeof_set_desc", "cbo_offsetof_set_desc", "cbo_last_error", "cbo_sweep_num_items",
+    "cbo_prior_workspace_bytes",
     "cbo_build_tables", "cbo_prior_precompute", "cbo_prior_eval", "cbo_posterior_fit", "cbo_sweep",
     "cbo_argmax_combine",
 ]
@@ -83,12 +84,14 @@ def load() -> C.CDLL:
     lib.cbo_sweep_num_items.argtypes = [P, C.c_int]
     lib.cbo_build_tables.argtypes = [P, C.c_int, C.c_void_p]
     lib.cbo_prior_precompute.argtypes = [P, C.c_int, C.c_void_p]
-    lib.cbo_prior_eval.argtypes = [P, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.cbo_prior_workspace_bytes.restype = C.c_size_t
+    lib.cbo_prior_workspace_bytes.argtypes = [P, C.c_int, C.c_int]
+    lib.cbo_prior_eval.argtypes = [P, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.cbo_posterior_fit.argtypes = [P, C.c_void_p, C.c_int, C.c_void_p]
     lib.cbo_sweep.argtypes = [P, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_void_p]
     lib.cbo_argmax_combine.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
-    for name in EXPORTS[5:]:
+    for name in EXPORTS[6:]:
         getattr(lib, name).restype = C.c_int
     if lib.cbo_abi_version() != CBO_ABI_VERSION:
         raise ImportError(f"ABI version mismatch: library {lib.cbo_abi_version()} != binding {CBO_ABI_VERSION}")

@@ -46,6 +46,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     extra = ["-Xptxas", "-v"] if verbose else []
+    extra += os.environ.get("CBO_NVCC_EXTRA", "").split()
 
     def compile_one(src: str) -> str:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))

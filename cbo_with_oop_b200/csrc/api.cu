@@ -23,16 +23,6 @@ int cuda_fail(cudaError_t e, const char* what) {
     return (int)e;
 }
 
-int prior_variant() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("CBO_PRIOR_VARIANT");
-        v = e ? atoi(e) : 0;
-        if (v < 0 || v > 2) v = 0;
-    }
-    return v;
-}
-
 int validate_sets(const cbo_set_desc* h_sets, int num_sets) {
     CBO_REQUIRE(h_sets != nullptr, "descriptor array is NULL");
     CBO_REQUIRE(num_sets >= 1 && num_sets <= 4096, "num_sets=%d outside [1,4096]", num_sets);
@@ -64,7 +54,8 @@ int validate_sets(const cbo_set_desc* h_sets, int num_sets) {
 
 int build_tables_impl(const cbo_set_desc*, int, cudaStream_t);
 int prior_precompute_impl(const cbo_set_desc*, int, cudaStream_t);
-int prior_eval_impl(const cbo_set_desc*, const cbo_set_desc*, int, int, cudaStream_t);
+int prior_eval_impl(const cbo_set_desc*, const cbo_set_desc*, int, int, void*, size_t, cudaStream_t);
+size_t prior_workspace_bytes_impl(const cbo_set_desc*, int, int);
 int posterior_fit_impl(const cbo_set_desc*, const cbo_set_desc*, int, cudaStream_t);
 int sweep_impl(const cbo_set_desc*, const cbo_set_desc*, int, double, int, cbo_set_best*, cbo_set_best*, cbo_sweep_result*,
                cudaStream_t);
@@ -108,7 +99,13 @@ int cbo_prior_precompute(const cbo_set_desc* h_sets, int num_sets, void* stream)
     return prior_precompute_impl(h_sets, num_sets, (cudaStream_t)stream);
 }
 
-int cbo_prior_eval(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_sets, int which, void* stream) {
+size_t cbo_prior_workspace_bytes(const cbo_set_desc* h_sets, int num_sets, int num_ctas) {
+    if (!h_sets || num_sets < 1 || num_ctas < 1) return 0;
+    return prior_workspace_bytes_impl(h_sets, num_sets, num_ctas);
+}
+
+int cbo_prior_eval(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_sets, int which, void* d_workspace,
+                   size_t workspace_bytes, void* stream) {
     if (int rc = validate_sets(h_sets, num_sets)) return rc;
     CBO_REQUIRE(d_sets != nullptr, "cbo_prior_eval: d_sets is NULL");
     CBO_REQUIRE(which == 0 || which == 1, "cbo_prior_eval: which=%d must be 0 (grid) or 1 (x_int)", which);
@@ -123,7 +120,7 @@ int cbo_prior_eval(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int n
             CBO_REQUIRE(S.u_int && S.m_int && S.v_int, "cbo_prior_eval: set %d has NULL u_int/m_int/v_int", s);
         }
     }
-    return prior_eval_impl(h_sets, d_sets, num_sets, which, (cudaStream_t)stream);
+    return prior_eval_impl(h_sets, d_sets, num_sets, which, d_workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int cbo_posterior_fit(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_sets, void* stream) {

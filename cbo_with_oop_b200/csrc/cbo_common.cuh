@@ -87,6 +87,11 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                  "l"(__cvta_generic_to_global(gmem_src)), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// Order this thread's generic-proxy writes (st.global / st.shared) before later async-proxy (TMA) accesses.
+__device__ __forceinline__ void fence_proxy_async() {
+    __threadfence();
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
 // arrive (without incrementing the pending count) once all prior cp.async of this thread have landed
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -101,11 +106,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
     return ok != 0;
 }
 // try_wait suspends the warp in hardware for a bounded time, so this is not a hot spin.  A pipeline bug must
-// not hang a shared GPU: after ~2^26 failed probes (tens of seconds) the kernel traps and the launch reports an error.
+// not hang a shared GPU: after 2^24 failed probes (seconds) the kernel traps and the launch reports an error.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
     unsigned spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) __trap();
+        if (++spins > (1u << 24)) __trap();
     }
 }
 template <int N>

@@ -160,6 +160,10 @@ class SweepEngine:
         # sweep scratch / outputs
         self._fill_descs()
         n_items = self.lib.cbo_sweep_num_items(self.h_sets, A) if A else 0
+        # prior-eval workspace: one scratch slot per SM (persistent kernel, one CTA per SM)
+        self.num_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        ws = self.lib.cbo_prior_workspace_bytes(self.h_sets, A, self.num_sms) if A else 0
+        self.prior_ws = torch.empty((max(ws, 256),), dtype=torch.uint8, device=self.device)
         self.tile_best = torch.empty((max(n_items, 1) * C.sizeof(SetBest),), dtype=torch.uint8, device=self.device)
         self.local_best = torch.empty((max(A, 1) * C.sizeof(SetBest),), dtype=torch.uint8, device=self.device)
         self.result = torch.empty((C.sizeof(SweepResult),), dtype=torch.uint8, device=self.device)
@@ -306,7 +310,8 @@ class SweepEngine:
     def prior_eval(self, which: int, local_ids=None):
         h, dptr, n = self._subset(local_ids)
         if n:
-            _lib.check(self.lib.cbo_prior_eval(h, dptr, n, which, self._stream()), "cbo_prior_eval")
+            _lib.check(self.lib.cbo_prior_eval(h, dptr, n, which, C.c_void_p(self.prior_ws.data_ptr()),
+                                               self.prior_ws.numel(), self._stream()), "cbo_prior_eval")
 
     def posterior_fit(self, local_ids=None):
         h, dptr, n = self._subset(local_ids)

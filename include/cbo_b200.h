@@ -135,8 +135,14 @@ CBO_API int cbo_prior_precompute(const cbo_set_desc* h_sets, int num_sets, void*
 /* K1b. causal prior m(x) = u.w, v(x) = s2 + noise - u^T M u.
  * which = 0: on the rank's slice of the tensor grid (writes m, v);
  * which = 1: on the interventional rows x_int (writes m_int, v_int).
- * Replaces DoCalculus.update_do_function (DoCalculus.py:34-66), index 0 and 1 together. */
-CBO_API int cbo_prior_eval(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_sets, int which, void* stream);
+ * Replaces DoCalculus.update_do_function (DoCalculus.py:34-66), index 0 and 1 together.
+ * The kernel is persistent (one CTA per SM); each CTA materialises the 128 x n_obs_pad table product of its
+ * current 128 candidates in a private slot of `d_workspace` (device memory, 256-byte aligned).  Size it with
+ * cbo_prior_workspace_bytes(h_sets, num_sets, num_ctas); num_ctas = the SM count uses the whole GPU, fewer slots
+ * run fewer CTAs, at least one slot is required. */
+CBO_API size_t cbo_prior_workspace_bytes(const cbo_set_desc* h_sets, int num_sets, int num_ctas);
+CBO_API int cbo_prior_eval(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_sets, int which,
+                           void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* K2. one CTA per set: Gram of the interventional rows (CausalRBF.K, causal_kernels.py:45-62, or RBF),
  * + (1e-10 + 1e-8) I, Cholesky with GPy's jitter-retry rule, alpha = Ky^-1 (y - m).
