@@ -92,6 +92,7 @@ class SweepEngine:
         self.keep = tuple(keep)
         self.ncap = int(n_int_capacity)
         self.timing = False
+        self.launches = 0            # kernels of libcbo_b200 launched so far (bench.py reports the per-step count)
         self.pinned_staging = pinned_staging
         for k in self.keep:
             if k not in ("mu", "var", "ei", "acq"):
@@ -220,40 +221,47 @@ class SweepEngine:
         self.d_sets = torch.frombuffer(raw, dtype=torch.uint8).to(self.device)
 
     # ------------------------------------------------------------------------------------------------
-    def _h2d(self, dst: torch.Tensor, arr: np.ndarray, key):
-        arr = np.ascontiguousarray(arr, dtype=np.float64).reshape(-1)
-        if arr.size == 0:
-            return 0
-        if self.pinned_staging:
-            st = self._pins.get(key)
+    def _h2d(self, dst: torch.Tensor, arr: np.ndarray, key, restage: bool):
+        """One input array to the device.  With pinned staging the host copy lives in page-locked memory (filled
+        when the array is (re)staged) and the transfer is an asynchronous DMA on the current stream."""
+        if not self.pinned_staging:
+            arr = np.ascontiguousarray(arr, dtype=np.float64).reshape(-1)
+            if arr.size:
+                dst[:arr.size].copy_(torch.from_numpy(arr))
+            return arr.nbytes
+        st = self._pins.get(key)
+        if st is None or restage:
+            arr = np.ascontiguousarray(arr, dtype=np.float64).reshape(-1)
             if st is None or st.numel() != arr.size:
                 st = torch.empty((arr.size,), dtype=torch.float64).pin_memory()
                 self._pins[key] = st
-            st.numpy()[:] = arr
-            dst[:arr.size].copy_(st, non_blocking=True)
-        else:
-            dst[:arr.size].copy_(torch.from_numpy(arr))
-        return arr.nbytes
+            if arr.size:
+                st.numpy()[:] = arr
+        if st.numel():
+            dst[:st.numel()].copy_(st, non_blocking=True)
+        return st.numel() * 8
 
-    def upload(self, what: str = "all") -> int:
-        """Copy the host inputs to the device (returns bytes moved).  what = 'all' | 'interventional'."""
+    def upload(self, what: str = "all", restage: bool = False) -> int:
+        """Copy the host inputs to the device; returns the bytes moved.  what = 'all' | 'interventional'.
+        restage=True re-reads the caller's NumPy arrays into the pinned staging buffers first (needed after the
+        caller changed them in place); otherwise the staged copies are what is transferred."""
         if not hasattr(self, "_pins"):
             self._pins: Dict[object, torch.Tensor] = {}
         total = 0
         for li, g in enumerate(self.active):
             pr, b = self.problems[g], self.buf[li]
-            total += self._h2d(b["x_int"], pr.x_int, (li, "x_int"))
-            total += self._h2d(b["y_int"], pr.y_int, (li, "y_int"))
+            total += self._h2d(b["x_int"], pr.x_int, (li, "x_int"), restage)
+            total += self._h2d(b["y_int"], pr.y_int, (li, "y_int"), restage)
             if what == "interventional":
                 continue
             for k in range(pr.d):
-                total += self._h2d(b[f"grid{k}"], pr.grid[k], (li, f"grid{k}"))
+                total += self._h2d(b[f"grid{k}"], pr.grid[k], (li, f"grid{k}"), restage)
             if pr.causal:
-                total += self._h2d(b["x_obs_int"], np.asarray(pr.x_obs_int).T, (li, "x_obs_int"))
-                total += self._h2d(b["x_obs_cond"], np.asarray(pr.x_obs_cond).T, (li, "x_obs_cond"))
-                total += self._h2d(b["mc_cond"], np.asarray(pr.mc_cond).T, (li, "mc_cond"))
-                total += self._h2d(b["alpha_obs"], pr.alpha_obs, (li, "alpha_obs"))
-                total += self._h2d(b["kyinv"], pr.kyinv, (li, "kyinv"))
+                total += self._h2d(b["x_obs_int"], np.asarray(pr.x_obs_int).T, (li, "x_obs_int"), restage)
+                total += self._h2d(b["x_obs_cond"], np.asarray(pr.x_obs_cond).T, (li, "x_obs_cond"), restage)
+                total += self._h2d(b["mc_cond"], np.asarray(pr.mc_cond).T, (li, "mc_cond"), restage)
+                total += self._h2d(b["alpha_obs"], pr.alpha_obs, (li, "alpha_obs"), restage)
+                total += self._h2d(b["kyinv"], pr.kyinv, (li, "kyinv"), restage)
         return total
 
     def set_interventional(self, g: int, x_int: np.ndarray, y_int: np.ndarray):
@@ -266,13 +274,17 @@ class SweepEngine:
         if g in self.local_of:
             li = self.local_of[g]
             self.h_sets[li].n_int = pr.x_int.shape[0]
-            self._h2d(self.buf[li]["x_int"], pr.x_int, (li, "x_int"))
-            self._h2d(self.buf[li]["y_int"], pr.y_int, (li, "y_int"))
+            self._h2d(self.buf[li]["x_int"], pr.x_int, (li, "x_int"), True)
+            self._h2d(self.buf[li]["y_int"], pr.y_int, (li, "y_int"), True)
             off = li * C.sizeof(SetDesc)
             raw = bytearray(bytes(self.h_sets[li]))
             self.d_sets[off:off + len(raw)].copy_(torch.frombuffer(raw, dtype=torch.uint8))
 
     # ------------------------------------------------------------------------------------------------
+    @property
+    def d2h_bytes_per_sweep(self) -> int:
+        return C.sizeof(SweepResult) + len(self.problems) * C.sizeof(SetBest)
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -301,22 +313,26 @@ class SweepEngine:
         h, _, n = self._subset(local_ids)
         if n:
             _lib.check(self.lib.cbo_build_tables(h, n, self._stream()), "cbo_build_tables")
+            self.launches += sum(h[i].d + 1 for i in range(n) if h[i].causal)
 
     def prior_precompute(self, local_ids=None):
         h, _, n = self._subset(local_ids)
         if n:
             _lib.check(self.lib.cbo_prior_precompute(h, n, self._stream()), "cbo_prior_precompute")
+            self.launches += sum((2 if h[i].c > 0 else 1) for i in range(n) if h[i].causal)
 
     def prior_eval(self, which: int, local_ids=None):
         h, dptr, n = self._subset(local_ids)
         if n:
             _lib.check(self.lib.cbo_prior_eval(h, dptr, n, which, C.c_void_p(self.prior_ws.data_ptr()),
                                                self.prior_ws.numel(), self._stream()), "cbo_prior_eval")
+            self.launches += 1 if any(h[i].causal for i in range(n)) else 0
 
     def posterior_fit(self, local_ids=None):
         h, dptr, n = self._subset(local_ids)
         if n:
             _lib.check(self.lib.cbo_posterior_fit(h, dptr, n, self._stream()), "cbo_posterior_fit")
+            self.launches += 1
 
     def _sweep_local(self, best: float, task: str):
         A = len(self.active)
@@ -327,6 +343,7 @@ class SweepEngine:
                                           1 if task == "min" else -1, C.c_void_p(self.tile_best.data_ptr()),
                                           C.c_void_p(self.local_best.data_ptr()), C.c_void_p(self.result.data_ptr()),
                                           self._stream()), "cbo_sweep")
+            self.launches += 3
 
     def _finish(self, events) -> SweepOutput:
         """Scatter the local per-set bests into the global table, all-gather over ranks (NCCL), combine on
@@ -346,6 +363,7 @@ class SweepEngine:
             src, nr = gb, 1
         _lib.check(self.lib.cbo_argmax_combine(C.c_void_p(src.data_ptr()), nr, S, C.c_void_p(gb.data_ptr()),
                                                C.c_void_p(self.result.data_ptr()), self._stream()), "cbo_argmax_combine")
+        self.launches += 1
         res_h = self.result.cpu().numpy().tobytes()      # device -> host read of the step's result (synchronises)
         best_h = gb.cpu().numpy().tobytes()
         r = SweepResult.from_buffer_copy(res_h)
