@@ -8,7 +8,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcbo_b200.so")
 
-CBO_ABI_VERSION = 1
+CBO_ABI_VERSION = 2
 CBO_MAX_D = 4
 CBO_MAX_C = 8
 CBO_MAX_NINT = 128
@@ -34,8 +34,9 @@ class SetDesc(C.Structure):
         ("tab", _dp * CBO_MAX_D), ("u_int", _dp), ("P", _dp), ("pbar", _dp), ("w", _dp), ("M", _dp),
         ("grid", _dp * CBO_MAX_D), ("x_int", _dp), ("y_int", _dp), ("m_int", _dp), ("v_int", _dp),
         ("L", _dp), ("alpha", _dp), ("sqrt_v_int", _dp), ("fit_info", _dp),
-        ("cost_fix", C.c_double), ("cost_variable", C.c_int32), ("reserved0", C.c_int32),
+        ("cost_fix", C.c_double), ("cost_variable", C.c_int32), ("prior_external", C.c_int32),
         ("m", _dp), ("v", _dp), ("mu", _dp), ("var", _dp), ("ei", _dp), ("acq", _dp),
+        ("points", _dp),
     ]
 
 

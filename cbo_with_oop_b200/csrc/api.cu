@@ -39,7 +39,8 @@ int validate_sets(const cbo_set_desc* h_sets, int num_sets) {
         CBO_REQUIRE(g == S.g_total, "set %d: g_total=%lld != prod p = %lld", s, (long long)S.g_total, g);
         CBO_REQUIRE(S.g_begin >= 0 && S.g_count >= 0 && S.g_begin + S.g_count <= S.g_total,
                     "set %d: slice [%lld,+%lld) outside the grid of %lld", s, (long long)S.g_begin, (long long)S.g_count, g);
-        if (S.causal) {
+        CBO_REQUIRE(!S.points || (S.p[0] == S.g_total), "set %d: explicit points need p[0] == g_total", s);
+        if (S.causal && !S.prior_external) {
             CBO_REQUIRE(S.n_obs >= 1 && S.n_obs_pad >= S.n_obs && S.n_obs_pad % CBO_NPAD == 0,
                         "set %d: n_obs=%d n_obs_pad=%d (pad must be a multiple of %d)", s, S.n_obs, S.n_obs_pad, CBO_NPAD);
             CBO_REQUIRE(S.c == 0 || (S.n_mc >= 1 && S.n_mc_pad >= S.n_mc && S.n_mc_pad % CBO_SPAD == 0),
@@ -77,7 +78,7 @@ long cbo_offsetof_set_desc(const char* field) {
     F(d) F(c) F(n_obs) F(n_obs_pad) F(n_mc) F(n_mc_pad) F(n_int) F(causal) F(p) F(g_total) F(g_begin) F(g_count)
     F(x_obs_int) F(x_obs_cond) F(mc_cond) F(alpha_obs) F(kyinv) F(ls_int) F(ls_cond) F(s2) F(noise)
     F(tab) F(u_int) F(P) F(pbar) F(w) F(M) F(grid) F(x_int) F(y_int) F(m_int) F(v_int) F(L) F(alpha) F(sqrt_v_int)
-    F(fit_info) F(cost_fix) F(cost_variable) F(reserved0) F(m) F(v) F(mu) F(var) F(ei) F(acq)
+    F(fit_info) F(cost_fix) F(cost_variable) F(prior_external) F(m) F(v) F(mu) F(var) F(ei) F(acq) F(points)
 #undef F
     return -1;
 }
@@ -111,11 +112,11 @@ int cbo_prior_eval(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int n
     CBO_REQUIRE(which == 0 || which == 1, "cbo_prior_eval: which=%d must be 0 (grid) or 1 (x_int)", which);
     for (int s = 0; s < num_sets; ++s) {
         const cbo_set_desc& S = h_sets[s];
-        if (!S.causal) continue;
+        if (!computes_prior(S)) continue;
         CBO_REQUIRE(S.M && S.w, "cbo_prior_eval: set %d has NULL M/w", s);
         if (which == 0) {
             CBO_REQUIRE(S.g_count == 0 || (S.m && S.v), "cbo_prior_eval: set %d has NULL m/v", s);
-            for (int k = 0; k < S.d; ++k) CBO_REQUIRE(S.tab[k], "cbo_prior_eval: set %d tab[%d] is NULL", s, k);
+            for (int k = 0; k < (S.points ? 1 : S.d); ++k) CBO_REQUIRE(S.tab[k], "cbo_prior_eval: set %d tab[%d] is NULL", s, k);
         } else {
             CBO_REQUIRE(S.u_int && S.m_int && S.v_int, "cbo_prior_eval: set %d has NULL u_int/m_int/v_int", s);
         }

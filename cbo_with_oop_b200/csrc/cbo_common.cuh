@@ -29,12 +29,15 @@ int cuda_fail(cudaError_t e, const char* what);
 
 int validate_sets(const cbo_set_desc* h_sets, int num_sets);
 
+// does the library compute the causal prior of this set (as opposed to non-causal sets / caller-supplied priors)?
+__host__ __device__ inline bool computes_prior(const cbo_set_desc& S) { return S.causal && !S.prior_external; }
+
 // Work-item kinds of the batched kernels.  Every batched launch is a flat list of items
 // (set 0 tiles, set 1 tiles, ...); host and device count them with the same function.
 enum { kItemsPriorGrid = 0, kItemsPriorTrain = 1, kItemsSweep = 2 };
 __host__ __device__ inline long long host_items(const cbo_set_desc& S, int kind) {
-    if (kind == kItemsPriorGrid) return S.causal ? (S.g_count + CBO_PRIOR_TILE - 1) / CBO_PRIOR_TILE : 0;
-    if (kind == kItemsPriorTrain) return S.causal ? (S.n_int + CBO_PRIOR_TILE - 1) / CBO_PRIOR_TILE : 0;
+    if (kind == kItemsPriorGrid) return computes_prior(S) ? (S.g_count + CBO_PRIOR_TILE - 1) / CBO_PRIOR_TILE : 0;
+    if (kind == kItemsPriorTrain) return computes_prior(S) ? (S.n_int + CBO_PRIOR_TILE - 1) / CBO_PRIOR_TILE : 0;
     return (S.g_count + CBO_SWEEP_TILE - 1) / CBO_SWEEP_TILE;
 }
 

@@ -31,7 +31,7 @@ namespace cbo {
 constexpr int kPriorWsHeader = 256;  // bytes reserved at the start of the workspace (work counter)
 
 __host__ __device__ inline long long prior_items(const cbo_set_desc& S, int which) {
-    if (!S.causal) return 0;
+    if (!computes_prior(S)) return 0;
     return ((which == 0 ? S.g_count : (long long)S.n_int) + CBO_PRIOR_TILE - 1) / CBO_PRIOR_TILE;
 }
 
@@ -98,7 +98,7 @@ prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, int which
         }
         const cbo_set_desc& S = sets[s];
         // effective problem: the tensor grid (which == 0) or the n_int interventional rows (which == 1)
-        const int d = which == 0 ? S.d : 1;
+        const int d = (which == 0 && !S.points) ? S.d : 1;  // explicit points and x_int use one row-per-point table
         const long long gbeg = which == 0 ? S.g_begin : 0, gcnt = which == 0 ? S.g_count : S.n_int;
         double* out_m = which == 0 ? S.m : S.m_int;
         double* out_v = which == 0 ? S.v : S.v_int;
@@ -116,7 +116,7 @@ prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, int which
 #pragma unroll
             for (int k = CBO_MAX_D - 1; k >= 0; --k) {
                 if (k < d) {
-                    const int pk = which == 0 ? S.p[k] : S.n_int;
+                    const long long pk = which == 0 ? (S.points ? S.g_total : (long long)S.p[k]) : (long long)S.n_int;
                     sRow[k * BM + r] = (int)(gg % pk) * Npad;
                     gg /= pk;
                 }
@@ -262,7 +262,7 @@ using PriorCfgA = PriorCfg<2, 4, 8, 4, 4>;   // 8 consumer warps + 1 producer wa
 static size_t prior_slot_doubles(const cbo_set_desc* h_sets, int num_sets) {
     int npad = 0;
     for (int s = 0; s < num_sets; ++s)
-        if (h_sets[s].causal && h_sets[s].n_obs_pad > npad) npad = h_sets[s].n_obs_pad;
+        if (computes_prior(h_sets[s]) && h_sets[s].n_obs_pad > npad) npad = h_sets[s].n_obs_pad;
     return (size_t)CBO_PRIOR_TILE * npad;
 }
 
@@ -275,9 +275,9 @@ int prior_eval_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int 
     long long total = 0;
     for (int s = 0; s < num_sets; ++s) {
         const cbo_set_desc& S = h_sets[s];
-        if (!S.causal) continue;
-        for (int k = 0; k < (which == 0 ? S.d : 1); ++k) {
-            const long long pk = which == 0 ? S.p[k] : S.n_int;
+        if (!computes_prior(S)) continue;
+        for (int k = 0; k < ((which == 0 && !S.points) ? S.d : 1); ++k) {
+            const long long pk = which == 0 ? (S.points ? S.g_total : (long long)S.p[k]) : (long long)S.n_int;
             CBO_REQUIRE(pk * (long long)S.n_obs_pad < 2147483647LL, "cbo_prior_eval: table %d of set %d too large", k, s);
         }
         CBO_REQUIRE((long long)CBO_PRIOR_TILE * S.n_obs_pad < 2147483647LL, "cbo_prior_eval: set %d n_obs_pad too large", s);

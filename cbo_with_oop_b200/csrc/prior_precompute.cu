@@ -164,7 +164,7 @@ int prior_precompute_impl(const cbo_set_desc* h_sets, int num_sets, cudaStream_t
     }
     for (int s = 0; s < num_sets; ++s) {
         const cbo_set_desc& S = h_sets[s];
-        if (!S.causal) continue;
+        if (!computes_prior(S)) continue;
         CBO_REQUIRE(S.kyinv && S.alpha_obs && S.M && S.w && S.pbar, "cbo_prior_precompute: set %d has a NULL pointer", s);
         if (S.c == 0) {
             nocond_kernel<<<dim3(8, S.n_obs_pad), 256, 0, st>>>(S.kyinv, S.alpha_obs, S.n_obs, S.n_obs_pad, S.s2, S.M, S.pbar, S.w);

@@ -56,7 +56,10 @@ sweep_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, double best, d
     int is_nan = 0;
     if (valid) {
         double x[CBO_MAX_D];
-        {
+        if (S.points) {  // explicit candidates
+#pragma unroll
+            for (int k = 0; k < CBO_MAX_D; ++k) x[k] = k < d ? S.points[gidx * d + k] : 0.0;
+        } else {
             long long gg = gidx;
 #pragma unroll
             for (int k = CBO_MAX_D - 1; k >= 0; --k) {
@@ -218,7 +221,7 @@ int sweep_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_s
         CBO_REQUIRE(S.n_int >= 1 && S.n_int <= CBO_MAX_NINT, "cbo_sweep: set %d n_int=%d outside [1,%d]", s, S.n_int, CBO_MAX_NINT);
         CBO_REQUIRE(S.L && S.alpha && S.x_int, "cbo_sweep: set %d has a NULL posterior pointer", s);
         CBO_REQUIRE(!S.causal || (S.m && S.v && S.sqrt_v_int), "cbo_sweep: causal set %d needs m/v/sqrt_v_int", s);
-        for (int k = 0; k < S.d; ++k) CBO_REQUIRE(S.grid[k], "cbo_sweep: set %d grid[%d] is NULL", s, k);
+        for (int k = 0; k < (S.points ? 0 : S.d); ++k) CBO_REQUIRE(S.grid[k], "cbo_sweep: set %d grid[%d] is NULL", s, k);
         total += host_items(S, kItemsSweep);
         if (S.n_int > nmax) nmax = S.n_int;
     }

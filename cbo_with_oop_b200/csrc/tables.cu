@@ -50,9 +50,20 @@ points_table_kernel(const double* __restrict__ x_int, int n_int, int d, const do
 int build_tables_impl(const cbo_set_desc* h_sets, int num_sets, cudaStream_t st) {
     for (int s = 0; s < num_sets; ++s) {
         const cbo_set_desc& S = h_sets[s];
-        if (!S.causal) continue;
+        if (!computes_prior(S)) continue;
         const unsigned gx = (S.n_obs_pad + 255) / 256;
-        for (int k = 0; k < S.d; ++k) {
+        const double il[CBO_MAX_D] = {1.0 / S.ls_int[0], S.d > 1 ? 1.0 / S.ls_int[1] : 0.0, S.d > 2 ? 1.0 / S.ls_int[2] : 0.0,
+                                      S.d > 3 ? 1.0 / S.ls_int[3] : 0.0};
+        if (S.points) {  // explicit candidates: one table with a row per candidate
+            CBO_REQUIRE(S.tab[0] && S.x_obs_int, "cbo_build_tables: set %d has a NULL table pointer", s);
+            CBO_REQUIRE(S.g_total < 2147483647LL / CBO_MAX_D, "cbo_build_tables: set %d has too many explicit points", s);
+            if (S.g_total > 0) {
+                const unsigned gy = (unsigned)(S.g_total < 1024 ? S.g_total : 1024);
+                points_table_kernel<<<dim3(gx, gy), 256, 0, st>>>(S.points, (int)S.g_total, S.d, S.x_obs_int, S.n_obs, S.n_obs_pad,
+                                                                  il[0], il[1], il[2], il[3], S.tab[0]);
+            }
+        }
+        for (int k = 0; k < (S.points ? 0 : S.d); ++k) {
             CBO_REQUIRE(S.tab[k] && S.grid[k] && S.x_obs_int, "cbo_build_tables: set %d has a NULL table/grid pointer", s);
             const unsigned gy = (unsigned)(S.p[k] < 1024 ? S.p[k] : 1024);
             table_kernel<<<dim3(gx, gy), 256, 0, st>>>(S.grid[k], S.p[k], S.x_obs_int + (size_t)k * S.n_obs, S.n_obs,
@@ -60,10 +71,8 @@ int build_tables_impl(const cbo_set_desc* h_sets, int num_sets, cudaStream_t st)
         }
         CBO_REQUIRE(S.u_int && S.x_int, "cbo_build_tables: set %d has a NULL u_int/x_int pointer", s);
         const unsigned gy = (unsigned)(S.n_int < 1024 ? S.n_int : 1024);
-        points_table_kernel<<<dim3(gx, gy), 256, 0, st>>>(S.x_int, S.n_int, S.d, S.x_obs_int, S.n_obs, S.n_obs_pad,
-                                                          1.0 / S.ls_int[0], S.d > 1 ? 1.0 / S.ls_int[1] : 0.0,
-                                                          S.d > 2 ? 1.0 / S.ls_int[2] : 0.0,
-                                                          S.d > 3 ? 1.0 / S.ls_int[3] : 0.0, S.u_int);
+        points_table_kernel<<<dim3(gx, gy), 256, 0, st>>>(S.x_int, S.n_int, S.d, S.x_obs_int, S.n_obs, S.n_obs_pad, il[0], il[1],
+                                                          il[2], il[3], S.u_int);
         CBO_CUDA(cudaGetLastError());
     }
     return 0;

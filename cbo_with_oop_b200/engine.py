@@ -41,10 +41,29 @@ class SetProblem:
     cost_variable: bool = False
     causal: bool = True
     name: str = ""
+    # Caller-supplied causal prior (e.g. produced by DoCalculus closures): m_int, v_int on x_int and, for a grid sweep,
+    # m_grid / v_grid over the whole tensor grid.  When set, the observational-GP fields above are ignored.
+    prior_external: bool = False
+    m_int: Optional[np.ndarray] = None
+    v_int: Optional[np.ndarray] = None
+    m_grid: Optional[np.ndarray] = None
+    v_grid: Optional[np.ndarray] = None
 
     @property
     def d(self) -> int:
         return len(self.grid)
+
+    @property
+    def computes_prior(self) -> bool:
+        return self.causal and not self.prior_external
+
+    @staticmethod
+    def with_external_prior(grid, x_int, y_int, m_int, v_int, m_grid=None, v_grid=None, cost_fix=1.0, cost_variable=False,
+                            name=""):
+        d = len(grid)
+        return SetProblem(np.zeros((0, d)), np.zeros((0, 0)), np.zeros((0, 0)), np.zeros(0), np.zeros((0, 0)), np.ones(d),
+                          np.zeros(0), 1.0, list(grid), x_int, y_int, cost_fix=cost_fix, cost_variable=cost_variable,
+                          causal=True, name=name, prior_external=True, m_int=m_int, v_int=v_int, m_grid=m_grid, v_grid=v_grid)
 
     @property
     def g_total(self) -> int:
@@ -98,7 +117,7 @@ class SweepEngine:
             if k not in ("mu", "var", "ei", "acq"):
                 raise ValueError(f"unknown array {k!r}")
         S = len(self.problems)
-        sizes = [SetSize(p.g_total, p.x_obs_int.shape[0] if p.causal else 0, p.x_int.shape[0]) for p in self.problems]
+        sizes = [SetSize(p.g_total, p.x_obs_int.shape[0] if p.computes_prior else 0, p.x_int.shape[0]) for p in self.problems]
         self.slices = partition(sizes, world_size)[rank]
         self.active = [s for s in range(S) if self.slices[s][1] > 0]   # global ids of the sets this rank touches
         self.local_of = {g: i for i, g in enumerate(self.active)}
@@ -118,7 +137,7 @@ class SweepEngine:
         p_rows = p_cols = 0
         for g in self.active:
             pr = self.problems[g]
-            if pr.causal and pr.x_obs_cond.shape[1] > 0:
+            if pr.computes_prior and pr.x_obs_cond.shape[1] > 0:
                 p_rows = max(p_rows, _round_up(pr.x_obs_int.shape[0], _lib.CBO_NPAD))
                 p_cols = max(p_cols, _round_up(pr.mc_cond.shape[0], _lib.CBO_SPAD))
         self.P = self._dev((p_rows * p_cols,)) if p_rows else None
@@ -141,7 +160,10 @@ class SweepEngine:
                 b[f"grid{k}"] = self._dev((len(pr.grid[k]),))
             for name in self.keep:
                 b[name] = self._dev((gc,))
-            if pr.causal:
+            if pr.causal and pr.prior_external:
+                b["m"] = self._dev((gc,), zero=True)
+                b["v"] = self._dev((gc,), zero=True)
+            if pr.computes_prior:
                 N, c, Smc = pr.x_obs_int.shape[0], pr.x_obs_cond.shape[1], pr.mc_cond.shape[0]
                 Np = _round_up(N, _lib.CBO_NPAD)
                 b["x_obs_int"] = self._dev((d * N,))
@@ -186,13 +208,15 @@ class SweepEngine:
                 D.p[k] = len(pr.grid[k]) if k < d else 1
             D.g_total, D.g_begin, D.g_count = pr.g_total, gb, gc
             D.cost_fix, D.cost_variable = float(pr.cost_fix), int(bool(pr.cost_variable))
+            D.prior_external = int(bool(pr.causal and pr.prior_external))
             ptr = lambda name: b[name].data_ptr() if name in b else None
             for k in range(d):
                 D.grid[k] = ptr(f"grid{k}")
             D.x_int, D.y_int, D.L, D.alpha = ptr("x_int"), ptr("y_int"), ptr("L"), ptr("alpha")
             D.sqrt_v_int, D.m_int, D.v_int, D.fit_info = ptr("sqrt_v_int"), ptr("m_int"), ptr("v_int"), ptr("fit_info")
             D.mu, D.var, D.ei, D.acq = ptr("mu"), ptr("var"), ptr("ei"), ptr("acq")
-            if pr.causal:
+            D.m, D.v = ptr("m"), ptr("v")
+            if pr.computes_prior:
                 N, c, Smc = pr.x_obs_int.shape[0], pr.x_obs_cond.shape[1], pr.mc_cond.shape[0]
                 D.c, D.n_obs, D.n_obs_pad = c, N, _round_up(N, _lib.CBO_NPAD)
                 D.n_mc, D.n_mc_pad = Smc, _round_up(max(Smc, 1), _lib.CBO_SPAD)
@@ -215,7 +239,6 @@ class SweepEngine:
                     D.tab[k] = ptr(f"tab{k}")
                 D.u_int, D.pbar, D.w, D.M = ptr("u_int"), ptr("pbar"), ptr("w"), ptr("M")
                 D.P = self.P.data_ptr() if (self.P is not None and c > 0) else None
-                D.m, D.v = ptr("m"), ptr("v")
         A = len(self.active)
         raw = bytearray(bytes(self.h_sets)) if A else bytearray(C.sizeof(SetDesc))
         self.d_sets = torch.frombuffer(raw, dtype=torch.uint8).to(self.device)
@@ -252,11 +275,18 @@ class SweepEngine:
             pr, b = self.problems[g], self.buf[li]
             total += self._h2d(b["x_int"], pr.x_int, (li, "x_int"), restage)
             total += self._h2d(b["y_int"], pr.y_int, (li, "y_int"), restage)
+            if pr.causal and pr.prior_external:
+                total += self._h2d(b["m_int"], pr.m_int, (li, "m_int"), restage)
+                total += self._h2d(b["v_int"], pr.v_int, (li, "v_int"), restage)
             if what == "interventional":
                 continue
+            if pr.causal and pr.prior_external and pr.m_grid is not None:
+                gb, gc = self.slices[g]
+                total += self._h2d(b["m"], np.asarray(pr.m_grid).reshape(-1)[gb:gb + gc], (li, "m"), restage)
+                total += self._h2d(b["v"], np.asarray(pr.v_grid).reshape(-1)[gb:gb + gc], (li, "v"), restage)
             for k in range(pr.d):
                 total += self._h2d(b[f"grid{k}"], pr.grid[k], (li, f"grid{k}"), restage)
-            if pr.causal:
+            if pr.computes_prior:
                 total += self._h2d(b["x_obs_int"], np.asarray(pr.x_obs_int).T, (li, "x_obs_int"), restage)
                 total += self._h2d(b["x_obs_cond"], np.asarray(pr.x_obs_cond).T, (li, "x_obs_cond"), restage)
                 total += self._h2d(b["mc_cond"], np.asarray(pr.mc_cond).T, (li, "mc_cond"), restage)
@@ -313,20 +343,20 @@ class SweepEngine:
         h, _, n = self._subset(local_ids)
         if n:
             _lib.check(self.lib.cbo_build_tables(h, n, self._stream()), "cbo_build_tables")
-            self.launches += sum(h[i].d + 1 for i in range(n) if h[i].causal)
+            self.launches += sum(h[i].d + 1 for i in range(n) if h[i].causal and not h[i].prior_external)
 
     def prior_precompute(self, local_ids=None):
         h, _, n = self._subset(local_ids)
         if n:
             _lib.check(self.lib.cbo_prior_precompute(h, n, self._stream()), "cbo_prior_precompute")
-            self.launches += sum((2 if h[i].c > 0 else 1) for i in range(n) if h[i].causal)
+            self.launches += sum((2 if h[i].c > 0 else 1) for i in range(n) if h[i].causal and not h[i].prior_external)
 
     def prior_eval(self, which: int, local_ids=None):
         h, dptr, n = self._subset(local_ids)
         if n:
             _lib.check(self.lib.cbo_prior_eval(h, dptr, n, which, C.c_void_p(self.prior_ws.data_ptr()),
                                                self.prior_ws.numel(), self._stream()), "cbo_prior_eval")
-            self.launches += 1 if any(h[i].causal for i in range(n)) else 0
+            self.launches += 1 if any(h[i].causal and not h[i].prior_external for i in range(n)) else 0
 
     def posterior_fit(self, local_ids=None):
         h, dptr, n = self._subset(local_ids)
@@ -356,8 +386,8 @@ class SweepEngine:
             idx = torch.as_tensor(self.active, device=self.device, dtype=torch.long)
             gv.index_copy_(0, idx, lv[:len(self.active)])
         if self.world > 1:
-            import torch.distributed as dist
-            dist.all_gather_into_tensor(self.gathered, gb, group=self.group)
+            from .dist import gather_set_bests
+            gather_set_bests(gb, self.gathered, self.world, self.group)
             src, nr = self.gathered, self.world
         else:
             src, nr = gb, 1
@@ -400,7 +430,7 @@ class SweepEngine:
             if g not in self.local_of:
                 continue
             li = [self.local_of[g]]
-            if self.problems[g].causal:
+            if self.problems[g].computes_prior:
                 self._timed("tables", lambda: self.build_tables(li), ev)
                 self._timed("prior_eval_train", lambda: self.prior_eval(1, li), ev)
             self._timed("posterior_fit", lambda: self.posterior_fit(li), ev)
@@ -408,6 +438,69 @@ class SweepEngine:
         return self._finish(ev)
 
     # ------------------------------------------------------------------------------------------------
+    def evaluate_points(self, g: int, X: np.ndarray, best: float = 0.0, task: str = "min", stages: str = "all",
+                        m_pts: Optional[np.ndarray] = None, v_pts: Optional[np.ndarray] = None) -> Dict[str, np.ndarray]:
+        """Evaluate global set g at arbitrary candidates X (m, d) with the set's CURRENT device state -- the explicit-point
+        twin of the grid sweep, behind model.predict(X), acquisition.evaluate(X) and the DoCalculus closures
+        (DoCalculus.py:34-66, causal_acquisition_functions.py:27-43).
+        stages = 'prior': only m(X), v(X) (needs tables + prior_precompute done);
+        stages = 'all'  : also mu, var, ei, acq (needs the posterior fit done).
+        A set with an external prior takes m_pts / v_pts from the caller."""
+        li = self.local_of[g]
+        pr, D0 = self.problems[g], self.h_sets[li]
+        X = np.ascontiguousarray(np.asarray(X, np.float64).reshape(-1, pr.d))
+        mtot = X.shape[0]
+        names = ["m", "v"] + (["mu", "var", "ei", "acq"] if stages == "all" else [])
+        out = {k: np.empty(mtot) for k in names}
+        if mtot == 0:
+            return out
+        Np = D0.n_obs_pad if pr.computes_prior else 0
+        chunk = mtot if not Np else max(_lib.CBO_PRIOR_TILE, min(mtot, (256 << 20) // (8 * Np) // 128 * 128))
+        dev = self.device
+        for a in range(0, mtot, chunk):
+            mc = min(chunk, mtot - a)
+            D = SetDesc.from_buffer_copy(bytes(D0))
+            pts = torch.from_numpy(X[a:a + mc].reshape(-1)).to(dev)
+            bufs = {k: torch.empty((mc,), dtype=torch.float64, device=dev) for k in names}
+            D.points = pts.data_ptr()
+            D.p[0] = mc
+            for k in range(1, _lib.CBO_MAX_D):
+                D.p[k] = 1
+            D.g_total, D.g_begin, D.g_count = mc, 0, mc
+            D.m, D.v = bufs["m"].data_ptr(), bufs["v"].data_ptr()
+            D.mu = bufs["mu"].data_ptr() if "mu" in bufs else None
+            D.var = bufs["var"].data_ptr() if "var" in bufs else None
+            D.ei = bufs["ei"].data_ptr() if "ei" in bufs else None
+            D.acq = bufs["acq"].data_ptr() if "acq" in bufs else None
+            tab0 = None
+            if pr.computes_prior:
+                tab0 = torch.empty((mc * Np,), dtype=torch.float64, device=dev)
+                D.tab[0] = tab0.data_ptr()
+            elif pr.causal:
+                if m_pts is None or v_pts is None:
+                    raise ValueError("a set with an external prior needs m_pts and v_pts")
+                bufs["m"].copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(m_pts, np.float64).reshape(-1)[a:a + mc])))
+                bufs["v"].copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(v_pts, np.float64).reshape(-1)[a:a + mc])))
+            h = (SetDesc * 1)(D)
+            d_desc = torch.frombuffer(bytearray(bytes(h)), dtype=torch.uint8).to(dev)
+            dptr, st = C.c_void_p(d_desc.data_ptr()), self._stream()
+            if pr.computes_prior:
+                _lib.check(self.lib.cbo_build_tables(h, 1, st), "cbo_build_tables")
+                _lib.check(self.lib.cbo_prior_eval(h, dptr, 1, 0, C.c_void_p(self.prior_ws.data_ptr()), self.prior_ws.numel(), st),
+                           "cbo_prior_eval")
+                self.launches += 3
+            if stages == "all":
+                n_items = self.lib.cbo_sweep_num_items(h, 1)
+                scratch = torch.empty(((n_items + 2) * C.sizeof(SetBest) + C.sizeof(SweepResult),), dtype=torch.uint8, device=dev)
+                base = scratch.data_ptr()
+                _lib.check(self.lib.cbo_sweep(h, dptr, 1, float(best), 1 if task == "min" else -1, C.c_void_p(base),
+                                              C.c_void_p(base + n_items * C.sizeof(SetBest)),
+                                              C.c_void_p(base + (n_items + 1) * C.sizeof(SetBest)), st), "cbo_sweep")
+                self.launches += 3
+            for k in names:
+                out[k][a:a + mc] = bufs[k].cpu().numpy()
+        return out
+
     def fetch(self, name: str, g: int) -> np.ndarray:
         """Device array of global set g as NumPy (parity tests / debugging)."""
         li = self.local_of[g]

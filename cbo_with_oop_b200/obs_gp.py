@@ -47,3 +47,63 @@ def fit_state(X: np.ndarray, y: np.ndarray, s2: float, ls, noise: float = 1e-2, 
     kyinv = 0.5 * (kyinv + kyinv.T)
     alpha = kyinv @ torch.as_tensor(y, device=device)
     return alpha.cpu().numpy(), kyinv.cpu().numpy()
+
+
+def neg_log_marginal_likelihood(theta, X, y, ard, noise):
+    """-log p(y | X, s2, l) and its gradient w.r.t. theta = log(s2), log(l) (l scalar or per-dimension).
+    Zero mean, RBF kernel, fixed Gaussian noise (utils.py:41-43)."""
+    N, D = X.shape
+    s2 = np.exp(theta[0])
+    ls = np.exp(theta[1:]) if ard else np.repeat(np.exp(theta[1]), D)
+    Z = X / ls
+    sq = np.sum(Z * Z, 1)
+    r2 = np.clip(sq[:, None] + sq[None, :] - 2.0 * (Z @ Z.T), 0.0, None)
+    np.fill_diagonal(r2, 0.0)
+    K = s2 * np.exp(-0.5 * r2)
+    Ky = K + (noise + GPY_JITTER) * np.eye(N)
+    try:
+        L = np.linalg.cholesky(Ky)
+    except np.linalg.LinAlgError:
+        return 1e25, np.zeros_like(theta)
+    alpha = scipy.linalg.cho_solve((L, True), y)
+    nll = 0.5 * y @ alpha + np.sum(np.log(np.diag(L))) + 0.5 * N * np.log(2 * np.pi)
+    Kinv = scipy.linalg.cho_solve((L, True), np.eye(N))
+    W = np.outer(alpha, alpha) - Kinv            # dL/dK = 0.5 * W
+    g = np.empty_like(theta)
+    g[0] = -0.5 * np.sum(W * K)                  # dK/dlog s2 = K
+    if ard:
+        for k in range(D):
+            dk = (Z[:, k][:, None] - Z[:, k][None, :]) ** 2   # dK/dlog l_k = K * dk
+            g[1 + k] = -0.5 * np.sum(W * K * dk)
+    else:
+        g[1] = -0.5 * np.sum(W * K * r2)
+    return nll, g
+
+
+def optimize_hyperparameters(X, y, s2=1.0, ls=1.0, ard=False, noise=1e-2, max_iters=1000, min_lengthscale=None,
+                             max_variance=None):
+    """Stand-in for GPy's `gp.optimize()` in fit_gaussian_process (utils.py:40-45): maximise the marginal
+    likelihood over the RBF variance and lengthscale(s), Gaussian noise fixed.  L-BFGS-B in log space from the
+    given start (one run, like GPy's default).  Host SciPy -- produces INPUTS of the sweep, not part of it."""
+    import scipy.optimize
+    X = np.asarray(X, np.float64)
+    y = np.asarray(y, np.float64).reshape(-1)
+    D = X.shape[1]
+    ls0 = np.broadcast_to(np.asarray(ls, np.float64).reshape(-1), (D,)) if ard else np.asarray(ls, np.float64).reshape(-1)[:1]
+    theta0 = np.concatenate([[np.log(s2)], np.log(ls0)])
+    # GPy optimises without bounds; +-12 in log space only keeps the search finite.  `min_lengthscale` (scalar or per
+    # dimension) is an optional floor: with the noise pinned to 1e-2 the likelihood of noisy data is maximised by a
+    # vanishing lengthscale, which makes the causal prior constant -- callers that want a usable prior set a floor.
+    bounds = [(-12.0, 12.0)] * theta0.size
+    if min_lengthscale is not None:
+        lo = np.log(np.broadcast_to(np.asarray(min_lengthscale, np.float64).reshape(-1), (theta0.size - 1,)))
+        bounds = [bounds[0]] + [(float(l), 12.0) for l in lo]
+        theta0[1:] = np.maximum(theta0[1:], lo)
+    if max_variance is not None:
+        bounds[0] = (-12.0, float(np.log(max_variance)))
+    res = scipy.optimize.minimize(neg_log_marginal_likelihood, theta0, args=(X, y, ard, noise), jac=True, method="L-BFGS-B",
+                                  bounds=bounds, options={"maxiter": max_iters})
+    th = res.x if np.isfinite(res.fun) and res.fun < 1e24 else theta0
+    s2_opt = float(np.exp(th[0]))
+    ls_opt = np.exp(th[1:]) if ard else np.repeat(np.exp(th[1]), D)
+    return s2_opt, ls_opt

@@ -30,7 +30,7 @@ extern "C" {
 #define CBO_API
 #endif
 
-#define CBO_ABI_VERSION 1
+#define CBO_ABI_VERSION 2
 #define CBO_MAX_D 4          /* intervened dimensions per exploration set (reference uses 1..3) */
 #define CBO_MAX_C 8          /* conditioning dimensions of an observational GP */
 #define CBO_MAX_NINT 128     /* interventional rows per set (reference: 10 .. ~50) */
@@ -87,7 +87,8 @@ typedef struct cbo_set_desc {
     /* ---- acquisition ----------------------------------------------------------------------------- */
     double cost_fix;           /* sum of the fixed costs of the set's variables (cost_functions.py:11-17) */
     int32_t cost_variable;     /* 1: add sum_k |x_k| per candidate (GraphInterface.py:46-50) */
-    int32_t reserved0;
+    int32_t prior_external;    /* 1: m_int, v_int, m, v are supplied by the caller (e.g. produced by the mean/variance
+                                  closures of DoCalculus); build_tables / prior_precompute / prior_eval skip the set */
     /* ---- per-candidate arrays, indexed by (g - g_begin) ----------------------------------------- */
     double* m;                 /* (g_count) prior mean       [cbo_prior_eval which=0]; required when causal */
     double* v;                 /* (g_count) prior variance */
@@ -95,6 +96,9 @@ typedef struct cbo_set_desc {
     double* var;               /* optional: posterior variance incl. 1e-10 noise */
     double* ei;                /* optional: expected improvement */
     double* acq;               /* optional: ei / cost */
+    /* ---- explicit candidates instead of a tensor grid (model.predict(X) / acquisition.evaluate(X) on arbitrary X) ---- */
+    const double* points;      /* NULL: tensor grid.  Otherwise (g_total, d) row-major candidates; then p[0] = g_total,
+                                  p[1..] = 1, grid[] is unused and tab[0] is the (g_total, n_obs_pad) exp table of the points */
 } cbo_set_desc;
 
 /* Result of one sweep on one rank. */

@@ -1,0 +1,71 @@
+"""GPU parity against the committed golden fixtures (tests/golden/golden_*.npz, produced by make_golden.py from
+the shipped data of the reference: BASELINE.json configs 1-3, and config 4 with synthetic observations).
+All exploration sets of a config go through ONE batched sweep; integer results must be bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import RTOL, rel_err
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_problems(z):
+    from cbo_with_oop_b200.engine import SetProblem
+    from cbo_with_oop_b200.obs_gp import fit_state
+    problems = []
+    for s in range(int(z["num_sets"])):
+        k = f"set{s}_"
+        xi, xc = z[k + "x_obs_int"], z[k + "x_obs_cond"]
+        ls_int, ls_cond, s2 = z[k + "ls_int"], z[k + "ls_cond"], float(z[k + "s2"])
+        if k + "kyinv" in z:
+            alpha, kyinv = z[k + "alpha_obs"], z[k + "kyinv"]
+        else:
+            alpha, kyinv = fit_state(np.hstack([xi, xc]), z[k + "y_obs"], s2, np.concatenate([ls_int, ls_cond]), 1e-2)
+            np.testing.assert_allclose(alpha, z[k + "alpha_obs"], rtol=1e-8, atol=1e-10 * np.abs(z[k + "alpha_obs"]).max())
+        grid = [np.linspace(lo, hi, int(p)) for lo, hi, p in z[k + "grid_lo_hi_p"]]
+        problems.append(SetProblem(x_obs_int=xi, x_obs_cond=xc, mc_cond=xc, alpha_obs=alpha, kyinv=kyinv, ls_int=ls_int,
+                                   ls_cond=ls_cond, s2=s2, grid=grid, x_int=z[k + "x_int"], y_int=z[k + "y_int"],
+                                   cost_fix=float(z[k + "cost_fix"]), name=str(z[k + "name"])))
+    return problems
+
+
+@pytest.mark.parametrize("config", ["toy", "complete", "simplified_coral", "coral_synth"])
+def test_golden_config(cuda_engine_ready, config):
+    path = os.path.join(GOLD, f"golden_{config}.npz")
+    z = np.load(path, allow_pickle=False)
+    from cbo_with_oop_b200.engine import SweepEngine
+    problems = load_problems(z)
+    eng = SweepEngine(problems, keep=("mu", "var", "ei", "acq"))
+    out = eng.sweep(float(z["best"]), str(z["task"]))
+    worst = {}
+    for s in range(len(problems)):
+        k = f"set{s}_"
+        keep = z[k + "keep"]
+        info = eng.fetch("fit_info", s)
+        assert info[1] == 0 and info[0] == int(z[k + "tries"])
+        kd = 1.0 + z[k + "vg"]
+        ei_scale = np.nanmax(np.abs(z[k + "ei"]))
+        errs = {
+            "m_int": rel_err(eng.fetch("m_int", s), z[k + "mI"], 1e-6).max(),
+            "v_int": rel_err(eng.fetch("v_int", s), z[k + "vI"], 1e-6).max(),
+            "L": rel_err(eng.fetch("L", s), z[k + "L"], 1e-6).max(),
+            "alpha": rel_err(eng.fetch("alpha", s), z[k + "alpha"], 1e-6 * np.abs(z[k + "alpha"]).max()).max(),
+            "m": rel_err(eng.fetch("m", s)[keep], z[k + "mg"], 1e-6).max(),
+            "v": rel_err(eng.fetch("v", s)[keep], z[k + "vg"], 1e-6).max(),
+            "mu": rel_err(eng.fetch("mu", s)[keep], z[k + "mu"], 1e-4).max(),
+            "var": rel_err(eng.fetch("var", s)[keep], z[k + "var"], 1e-4 * kd).max(),
+            "ei": np.nanmax(rel_err(eng.fetch("ei", s)[keep], z[k + "ei"], 1e-6 * ei_scale)),
+            "acq": np.nanmax(rel_err(eng.fetch("acq", s)[keep], z[k + "acq"], 1e-6 * ei_scale)),
+        }
+        for name, e in errs.items():
+            worst[name] = max(worst.get(name, 0.0), float(e))
+            assert e <= RTOL, f"{config} set {s} ({z[k + 'name']}) {name}: {e:.3e}"
+        assert out.set_indices[s] == int(z[k + "idx"]), \
+            f"{config} set {s}: argmax {out.set_indices[s]} != golden {int(z[k + 'idx'])} (top-2 gap {float(z[k + 'top2_gap']):.1e})"
+        np.testing.assert_allclose(out.set_values[s], float(z[k + "val"]), rtol=RTOL)
+    assert out.set == int(z["selected_set"])
+    assert out.n_nan == sum(int(z[f"set{s}_n_nan"]) for s in range(len(problems)))
+    print(config, {k: f"{v:.1e}" for k, v in worst.items()})
