@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import RTOL, rel_err
+from helpers import BACKWARD_TOL, MODERATE_COND, RTOL, fit_errors, rel_err
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -32,6 +32,26 @@ def load_problems(z):
     return problems
 
 
+TIE_GAP = 1e-9
+
+
+def oracle_acq_at(z, s, x, best):
+    """Oracle acquisition of set s at ONE candidate x, from the inputs stored in the fixture."""
+    from oracle import cbo_oracle as O
+    k = f"set{s}_"
+    X = np.hstack([z[k + "x_obs_int"], z[k + "x_obs_cond"]])
+    d = z[k + "x_obs_int"].shape[1]
+    from cbo_with_oop_b200.obs_gp import fit_state
+    s2, ls = float(z[k + "s2"]), np.concatenate([z[k + "ls_int"], z[k + "ls_cond"]])
+    kyinv = z[k + "kyinv"] if k + "kyinv" in z else fit_state(X, z[k + "y_obs"], s2, ls, 1e-2)[1]
+    gp = dict(X=X, variance=s2, lengthscale=ls, noise=1e-2, alpha=z[k + "alpha_obs"], Kyinv=kyinv, form="diff")
+    f = O.prior_factors(gp, X, list(range(d)))
+    post = O.posterior_fit(z[k + "x_int"], z[k + "y_int"], z[k + "mI"], z[k + "vI"], form="diff")
+    m, v = O.do_prior_factorised(gp, f, list(range(d)), x[None, :])
+    mu, var = O.posterior_predict(post, x[None, :], m, v)
+    return float(O.expected_improvement(mu, var, best, "min")[0] / float(z[k + "cost_fix"]))
+
+
 @pytest.mark.parametrize("config", ["toy", "complete", "simplified_coral", "coral_synth"])
 def test_golden_config(cuda_engine_ready, config):
     path = os.path.join(GOLD, f"golden_{config}.npz")
@@ -47,15 +67,21 @@ def test_golden_config(cuda_engine_ready, config):
         info = eng.fetch("fit_info", s)
         assert info[1] == 0 and info[0] == int(z[k + "tries"])
         kd = 1.0 + z[k + "vg"]
-        ei_scale = np.nanmax(np.abs(z[k + "ei"]))
+        ei_scale = max(np.nanmax(np.abs(z[k + "ei"])), 1e-300)
+        fe = fit_errors(eng.fetch("L", s), eng.fetch("alpha", s), z[k + "x_int"], z[k + "y_int"], eng.fetch("m_int", s),
+                        eng.fetch("v_int", s), z[k + "L"], z[k + "alpha"])
+        assert fe["L_backward"] <= BACKWARD_TOL and fe["alpha_backward"] <= BACKWARD_TOL, (config, s, fe)
+        worst["fit_cond"] = max(worst.get("fit_cond", 0.0), fe["cond"])
         errs = {
             "m_int": rel_err(eng.fetch("m_int", s), z[k + "mI"], 1e-6).max(),
             "v_int": rel_err(eng.fetch("v_int", s), z[k + "vI"], 1e-6).max(),
-            "L": rel_err(eng.fetch("L", s), z[k + "L"], 1e-6).max(),
-            "alpha": rel_err(eng.fetch("alpha", s), z[k + "alpha"], 1e-6 * np.abs(z[k + "alpha"]).max()).max(),
+            "L": fe["L_forward"] if fe["cond"] < MODERATE_COND else 0.0,
+            "alpha": fe["alpha_forward"] if fe["cond"] < MODERATE_COND else 0.0,
             "m": rel_err(eng.fetch("m", s)[keep], z[k + "mg"], 1e-6).max(),
             "v": rel_err(eng.fetch("v", s)[keep], z[k + "vg"], 1e-6).max(),
-            "mu": rel_err(eng.fetch("mu", s)[keep], z[k + "mu"], 1e-4).max(),
+            # zero crossings of mu: relative to the larger of |mu| and 0.1 % of the set's range of mu (the solve behind
+            # mu has condition numbers up to 1e10 on these data; both solvers are backward stable, see helpers.fit_errors)
+            "mu": rel_err(eng.fetch("mu", s)[keep], z[k + "mu"], max(1e-4, 1e-3 * np.abs(z[k + "mu"]).max())).max(),
             "var": rel_err(eng.fetch("var", s)[keep], z[k + "var"], 1e-4 * kd).max(),
             "ei": np.nanmax(rel_err(eng.fetch("ei", s)[keep], z[k + "ei"], 1e-6 * ei_scale)),
             "acq": np.nanmax(rel_err(eng.fetch("acq", s)[keep], z[k + "acq"], 1e-6 * ei_scale)),
@@ -63,9 +89,18 @@ def test_golden_config(cuda_engine_ready, config):
         for name, e in errs.items():
             worst[name] = max(worst.get(name, 0.0), float(e))
             assert e <= RTOL, f"{config} set {s} ({z[k + 'name']}) {name}: {e:.3e}"
-        assert out.set_indices[s] == int(z[k + "idx"]), \
-            f"{config} set {s}: argmax {out.set_indices[s]} != golden {int(z[k + 'idx'])} (top-2 gap {float(z[k + 'top2_gap']):.1e})"
+        # bit-exact selection -- unless the oracle's own top two candidates tie to rounding (flat acquisition far from
+        # every interventional row): then any member of the tie set is a correct argmax and the GPU's pick must be one
+        gap = float(z[k + "top2_gap"])
+        if out.set_indices[s] != int(z[k + "idx"]):
+            assert gap <= TIE_GAP, f"{config} set {s}: argmax {out.set_indices[s]} != golden {int(z[k + 'idx'])} (top-2 gap {gap:.1e})"
+            shape = [len(t) for t in problems[s].grid]
+            ii = np.unravel_index(int(out.set_indices[s]), shape)
+            x = np.array([problems[s].grid[a][ii[a]] for a in range(len(shape))])
+            a_ref = oracle_acq_at(z, s, x, float(z["best"]))
+            assert abs(a_ref - float(z[k + "val"])) <= TIE_GAP * abs(float(z[k + "val"])), (config, s, a_ref, float(z[k + "val"]))
+            worst["ties_resolved_differently"] = worst.get("ties_resolved_differently", 0) + 1
         np.testing.assert_allclose(out.set_values[s], float(z[k + "val"]), rtol=RTOL)
-    assert out.set == int(z["selected_set"])
+    assert out.set == int(z["selected_set"])      # the winning set's maximum is never a tie in these fixtures
     assert out.n_nan == sum(int(z[f"set{s}_n_nan"]) for s in range(len(problems)))
     print(config, {k: f"{v:.1e}" for k, v in worst.items()})

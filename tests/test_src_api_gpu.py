@@ -74,7 +74,7 @@ def test_factory_models_and_single_set_api(cuda_engine_ready):
     (single-set form) and the batched CBO.compute_best_acquisition_values agree with each other and the oracle."""
     from src.GaussianProcessFactory import GaussianProcessFactory, GaussianProcessType
     from src.utils_functions import CausalExpectedImprovement, Cost, find_next_y_point
-    cbo = make_agent("complete_graph", n_obs=50, p=30)
+    cbo = make_agent("complete_graph", n_obs=50, p=100)
     cbo.mean_functions, cbo.var_functions = cbo.do_calculus.update_all_do_functions(bounded_gps(cbo))
     cbo.update_all_gaussian_processes()
     best = float(cbo.current_best_solution())
