@@ -200,6 +200,7 @@ def run_ours(args, world, rank, local_rank):
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     from cbo_with_oop_b200.engine import SetProblem, SweepEngine
