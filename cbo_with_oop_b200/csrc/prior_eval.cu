@@ -30,9 +30,23 @@ namespace cbo {
 
 constexpr int kPriorWsHeader = 256;  // bytes reserved at the start of the workspace (work counter)
 
-__host__ __device__ inline long long prior_items(const cbo_set_desc& S, int which) {
+constexpr int kMaxSplit = 64;        // upper bound of the J split
+constexpr int kPartialDoubles = 2 * CBO_PRIOR_TILE;   // one (q, m) partial per row of a work item
+
+__host__ __device__ inline long long prior_tiles(const cbo_set_desc& S, int which) {
     if (!computes_prior(S)) return 0;
     return ((which == 0 ? S.g_count : (long long)S.n_int) + CBO_PRIOR_TILE - 1) / CBO_PRIOR_TILE;
+}
+// J split of one set: when a launch has too few 128-candidate tiles to fill the GPU (the interventional rows, small
+// grids) the column blocks of M are dealt to `ns` work items per tile, folded (jb mod 2ns in {sp, 2ns-1-sp}) so that the
+// triangular cost is balanced; the partial row sums are combined in a fixed order by prior_finalize_kernel.
+__host__ __device__ inline int prior_nsplit(const cbo_set_desc& S, int nsplit) {
+    const int nJ = (S.n_obs + kMBlkRows - 1) / kMBlkRows;
+    const int cap = nJ / 2 > 1 ? nJ / 2 : 1;
+    return nsplit < cap ? nsplit : cap;
+}
+__host__ __device__ inline long long prior_items(const cbo_set_desc& S, int which, int nsplit) {
+    return prior_tiles(S, which) * prior_nsplit(S, nsplit);
 }
 
 template <int WM_, int WN_, int MA_, int NB_, int STAGES_>
@@ -52,8 +66,8 @@ struct PriorCfg {
 
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::NT, 1)
-prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, int which, int total_items,
-                  unsigned char* __restrict__ ws, size_t slot_doubles) {
+prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, int which, int nsplit, int total_items,
+                  int* __restrict__ counter, double* __restrict__ partials, double* __restrict__ scratch_base, size_t slot_doubles) {
     constexpr int BM = Cfg::BM, BN = Cfg::BN, MA = Cfg::MA, NB = Cfg::NB, WN = Cfg::WN, NT = Cfg::NT;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int KB_PER_J = BN / kBK;
@@ -69,8 +83,7 @@ prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, int which
     uint64_t* empty = bars + STAGES;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int* counter = reinterpret_cast<int*>(ws);
-    double* __restrict__ scratch = reinterpret_cast<double*>(ws + kPriorWsHeader) + (size_t)blockIdx.x * slot_doubles;
+    double* __restrict__ scratch = scratch_base + (size_t)blockIdx.x * slot_doubles;
 
     if (tid == 0) {
         for (int i = 0; i < STAGES; ++i) {
@@ -89,14 +102,17 @@ prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, int which
         const int item = *sItem;
         if (item >= total_items) break;
 
-        // flat work item -> (set, tile)
-        int tile = item, s = 0;
+        // flat work item -> (set, tile, J split)
+        int local = item, s = 0;
         for (; s < num_sets - 1; ++s) {
-            const int cnt = (int)prior_items(sets[s], which);
-            if (tile < cnt) break;
-            tile -= cnt;
+            const int cnt = (int)prior_items(sets[s], which, nsplit);
+            if (local < cnt) break;
+            local -= cnt;
         }
         const cbo_set_desc& S = sets[s];
+        const int ns = prior_nsplit(S, nsplit);
+        const int tile = local / ns, sp = local % ns;
+        auto mine = [&](int jb) { const int r = jb % (2 * ns); return r == sp || r == 2 * ns - 1 - sp; };
         // effective problem: the tensor grid (which == 0) or the n_int interventional rows (which == 1)
         const int d = (which == 0 && !S.points) ? S.d : 1;  // explicit points and x_int use one row-per-point table
         const long long gbeg = which == 0 ? S.g_begin : 0, gcnt = which == 0 ? S.g_count : S.n_int;
@@ -173,6 +189,7 @@ prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, int which
             if (lane == 0) {
 #pragma unroll 1
                 for (int jb = 0; jb < nJ; ++jb) {
+                    if (!mine(jb)) continue;
                     const int nk = (jb + 1) * KB_PER_J;
 #pragma unroll 1
                     for (int kt = 0; kt < nk; ++kt) {
@@ -199,6 +216,7 @@ prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, int which
 
 #pragma unroll 1
             for (int jb = 0; jb < nJ; ++jb) {
+                if (!mine(jb)) continue;
                 const int nk = (jb + 1) * KB_PER_J, noff = jb * KB_PER_J;
 #pragma unroll 1
                 for (int kt = 0; kt < nk; ++kt) {
@@ -245,14 +263,48 @@ prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, int which
         __syncthreads();
         for (int r = tid; r < BM; r += NT) {
             const long long loc = (long long)tile * BM + r;
-            if (loc < gcnt) {
-                double qs = 0.0, ms = 0.0;
+            double qs = 0.0, ms = 0.0;
 #pragma unroll
-                for (int x = 0; x < WN; ++x) { qs += sRed[x * BM + r]; ms += sRed[(WN + x) * BM + r]; }
+            for (int x = 0; x < WN; ++x) { qs += sRed[x * BM + r]; ms += sRed[(WN + x) * BM + r]; }
+            if (ns > 1) {              // partial sums of this J split; prior_finalize_kernel adds them up
+                partials[(size_t)item * kPartialDoubles + r] = qs;
+                partials[(size_t)item * kPartialDoubles + BM + r] = ms;
+            } else if (loc < gcnt) {
                 out_m[loc] = ms;
                 out_v[loc] = (S.s2 + S.noise) - qs;
             }
         }
+    }
+}
+
+// Adds the J-split partials of every (set, tile) in split order (deterministic) and writes m, v.
+__global__ void __launch_bounds__(CBO_PRIOR_TILE)
+prior_finalize_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, int which, int nsplit,
+                      const double* __restrict__ partials) {
+    int base = 0;
+    for (int s = 0; s < num_sets; ++s) {
+        const cbo_set_desc& S = sets[s];
+        const int ns = prior_nsplit(S, nsplit), tiles = (int)prior_tiles(S, which);
+        if (ns > 1) {
+            const long long gcnt = which == 0 ? S.g_count : S.n_int;
+            double* out_m = which == 0 ? S.m : S.m_int;
+            double* out_v = which == 0 ? S.v : S.v_int;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                const int r = threadIdx.x;
+                const long long loc = (long long)tile * CBO_PRIOR_TILE + r;
+                if (loc < gcnt) {
+                    double qs = 0.0, ms = 0.0;
+                    for (int sp = 0; sp < ns; ++sp) {
+                        const double* p = partials + (size_t)(base + tile * ns + sp) * kPartialDoubles;
+                        qs += p[r];
+                        ms += p[CBO_PRIOR_TILE + r];
+                    }
+                    out_m[loc] = ms;
+                    out_v[loc] = (S.s2 + S.noise) - qs;
+                }
+            }
+        }
+        base += tiles * ns;
     }
 }
 
@@ -266,13 +318,17 @@ static size_t prior_slot_doubles(const cbo_set_desc* h_sets, int num_sets) {
     return (size_t)CBO_PRIOR_TILE * npad;
 }
 
+// workspace = [256 B header: work counter][partials: (4 ctas + 64) items][ctas scratch slots]
+static size_t prior_partial_items(long long ctas) { return (size_t)(4 * ctas + kMaxSplit); }
+
 size_t prior_workspace_bytes_impl(const cbo_set_desc* h_sets, int num_sets, int num_ctas) {
-    return kPriorWsHeader + (size_t)num_ctas * prior_slot_doubles(h_sets, num_sets) * sizeof(double);
+    return kPriorWsHeader + prior_partial_items(num_ctas) * kPartialDoubles * sizeof(double) +
+           (size_t)num_ctas * prior_slot_doubles(h_sets, num_sets) * sizeof(double);
 }
 
 int prior_eval_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_sets, int which, void* d_ws,
                     size_t ws_bytes, cudaStream_t st) {
-    long long total = 0;
+    long long tiles = 0;
     for (int s = 0; s < num_sets; ++s) {
         const cbo_set_desc& S = h_sets[s];
         if (!computes_prior(S)) continue;
@@ -281,20 +337,34 @@ int prior_eval_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int 
             CBO_REQUIRE(pk * (long long)S.n_obs_pad < 2147483647LL, "cbo_prior_eval: table %d of set %d too large", k, s);
         }
         CBO_REQUIRE((long long)CBO_PRIOR_TILE * S.n_obs_pad < 2147483647LL, "cbo_prior_eval: set %d n_obs_pad too large", s);
-        total += prior_items(S, which);
+        tiles += prior_tiles(S, which);
     }
-    CBO_REQUIRE(total < 2147483647LL, "cbo_prior_eval: too many work items");
-    if (total == 0) return 0;
+    if (tiles == 0) return 0;
     const size_t slot = prior_slot_doubles(h_sets, num_sets);
-    CBO_REQUIRE(d_ws != nullptr && ws_bytes >= kPriorWsHeader + slot * sizeof(double),
-                "cbo_prior_eval: workspace of %zu bytes cannot hold one scratch slot (%zu bytes); see cbo_prior_workspace_bytes",
-                ws_bytes, kPriorWsHeader + slot * sizeof(double));
+    const size_t fixed = kPriorWsHeader + (size_t)kMaxSplit * kPartialDoubles * sizeof(double);
+    const size_t per_cta = 4 * kPartialDoubles * sizeof(double) + slot * sizeof(double);
+    CBO_REQUIRE(d_ws != nullptr && ws_bytes >= fixed + per_cta,
+                "cbo_prior_eval: workspace of %zu bytes cannot hold one scratch slot (%zu bytes needed); see cbo_prior_workspace_bytes",
+                ws_bytes, fixed + per_cta);
     int dev = 0, sms = 0;
     CBO_CUDA(cudaGetDevice(&dev));
     CBO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    long long ctas = (long long)((ws_bytes - kPriorWsHeader) / (slot * sizeof(double)));
+    long long ctas = (long long)((ws_bytes - fixed) / per_cta);
     if (ctas > sms) ctas = sms;      // one CTA per SM (shared memory bound); more slots than SMs are not used
-    if (ctas > total) ctas = total;
+    // too few tiles to fill the GPU twice over: split the column blocks of M between work items
+    int nsplit = 1;
+    if (tiles < 2 * ctas) {
+        nsplit = (int)((2 * ctas + tiles - 1) / tiles);
+        if (nsplit > kMaxSplit) nsplit = kMaxSplit;
+    }
+    long long total = 0;
+    for (int s = 0; s < num_sets; ++s) total += prior_items(h_sets[s], which, nsplit);
+    CBO_REQUIRE(total < 2147483647LL, "cbo_prior_eval: too many work items");
+    CBO_REQUIRE(nsplit == 1 || (size_t)total <= prior_partial_items(ctas), "cbo_prior_eval: internal: partial buffer too small");
+    const long long grid = ctas < total ? ctas : total;
+    unsigned char* ws = reinterpret_cast<unsigned char*>(d_ws);
+    double* partials = reinterpret_cast<double*>(ws + kPriorWsHeader);
+    double* scratch = partials + prior_partial_items(ctas) * kPartialDoubles;
     auto kern = prior_eval_kernel<PriorCfgA>;
     static bool configured = false;
     if (!configured) {
@@ -302,9 +372,13 @@ int prior_eval_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int 
         configured = true;
     }
     CBO_CUDA(cudaMemsetAsync(d_ws, 0, kPriorWsHeader, st));
-    kern<<<(unsigned)ctas, PriorCfgA::NT, PriorCfgA::SMEM, st>>>(d_sets, num_sets, which, (int)total,
-                                                                 reinterpret_cast<unsigned char*>(d_ws), slot);
+    kern<<<(unsigned)grid, PriorCfgA::NT, PriorCfgA::SMEM, st>>>(d_sets, num_sets, which, nsplit, (int)total,
+                                                                 reinterpret_cast<int*>(ws), partials, scratch, slot);
     CBO_CUDA(cudaGetLastError());
+    if (nsplit > 1) {
+        prior_finalize_kernel<<<(unsigned)(tiles < 1024 ? tiles : 1024), CBO_PRIOR_TILE, 0, st>>>(d_sets, num_sets, which, nsplit, partials);
+        CBO_CUDA(cudaGetLastError());
+    }
     return 0;
 }
 

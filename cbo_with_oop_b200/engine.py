@@ -356,7 +356,10 @@ class SweepEngine:
         if n:
             _lib.check(self.lib.cbo_prior_eval(h, dptr, n, which, C.c_void_p(self.prior_ws.data_ptr()),
                                                self.prior_ws.numel(), self._stream()), "cbo_prior_eval")
-            self.launches += 1 if any(h[i].causal and not h[i].prior_external for i in range(n)) else 0
+            act = [h[i] for i in range(n) if h[i].causal and not h[i].prior_external]
+            tiles = sum(-(-(a.g_count if which == 0 else a.n_int) // _lib.CBO_PRIOR_TILE) for a in act)
+            # one persistent kernel; plus the partial-sum finalize when the column blocks had to be split to fill the GPU
+            self.launches += (1 + (1 if tiles < 2 * self.num_sms else 0)) if tiles else 0
 
     def posterior_fit(self, local_ids=None):
         h, dptr, n = self._subset(local_ids)
