@@ -8,7 +8,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcbo_b200.so")
 
-CBO_ABI_VERSION = 2
+CBO_ABI_VERSION = 3
 CBO_MAX_D = 4
 CBO_MAX_C = 8
 CBO_MAX_NINT = 128
@@ -36,6 +36,7 @@ class SetDesc(C.Structure):
         ("L", _dp), ("alpha", _dp), ("sqrt_v_int", _dp), ("fit_info", _dp),
         ("cost_fix", C.c_double), ("cost_variable", C.c_int32), ("prior_external", C.c_int32),
         ("m", _dp), ("v", _dp), ("mu", _dp), ("var", _dp), ("ei", _dp), ("acq", _dp),
+        ("posterior_cached", C.c_int32), ("reserved1", C.c_int32),
         ("points", _dp),
     ]
 

@@ -18,6 +18,62 @@ namespace cbo {
 
 constexpr int kSweepThreads = CBO_SWEEP_TILE;
 
+// Shared-memory image of one set's posterior: L^-1 is NOT formed; the forward substitution reads L rows (packed lower
+// triangle) as warp-wide broadcasts.
+struct SweepSmem {
+    double* Lp;    // packed lower triangle, row i at i(i+1)/2
+    double* al;    // alpha
+    double* sv;    // sqrt(v_int)
+    double* xs;    // x_int, n x d
+    double* tcol;  // [n][kSweepThreads] workspace of the generic path
+};
+
+// Posterior mean and |L^-1 k*|^2 of one candidate.  NREG > 0: n <= NREG and the solution vector lives in registers
+// (fully unrolled, one broadcast LDS per FMA); NREG == 0: any n <= CBO_MAX_NINT, the vector lives in a shared-memory
+// column owned by the thread.
+template <int NREG>
+__device__ __forceinline__ void posterior_at(const SweepSmem& sm, int n, int d, const double (&x)[CBO_MAX_D], double svg,
+                                             int tid, double& mu, double& ss) {
+    mu = 0.0; ss = 0.0;
+    if constexpr (NREG > 0) {
+        double t[NREG];
+#pragma unroll
+        for (int i = 0; i < NREG; ++i) {
+            if (i < n) {
+                double r2 = 0.0;
+#pragma unroll
+                for (int k = 0; k < CBO_MAX_D; ++k) {
+                    if (k < d) { const double q = x[k] - sm.xs[i * d + k]; r2 = fma(q, q, r2); }
+                }
+                const double ks = exp(-0.5 * r2) + sm.sv[i] * svg;
+                mu = fma(ks, sm.al[i], mu);
+                const double* __restrict__ Li = sm.Lp + i * (i + 1) / 2;
+                double a = ks;
+#pragma unroll
+                for (int j = 0; j < i; ++j) a = fma(-Li[j], t[j], a);
+                t[i] = a / Li[i];
+                ss = fma(t[i], t[i], ss);
+            }
+        }
+    } else {
+        for (int i = 0; i < n; ++i) {
+            double r2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < CBO_MAX_D; ++k) {
+                if (k < d) { const double q = x[k] - sm.xs[i * d + k]; r2 = fma(q, q, r2); }
+            }
+            const double ks = exp(-0.5 * r2) + sm.sv[i] * svg;
+            mu = fma(ks, sm.al[i], mu);
+            const double* __restrict__ Li = sm.Lp + i * (i + 1) / 2;
+            double a = ks;
+            for (int j = 0; j < i; ++j) a = fma(-Li[j], sm.tcol[j * kSweepThreads + tid], a);
+            const double tt = a / Li[i];
+            sm.tcol[i * kSweepThreads + tid] = tt;
+            ss = fma(tt, tt, ss);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kSweepThreads)
 sweep_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, double best, double task_sign,
              cbo_set_best* __restrict__ tile_best) {
@@ -27,26 +83,30 @@ sweep_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, double best, d
     const cbo_set_desc& S = sets[s];
     const int n = S.n_int, d = S.d, tid = threadIdx.x;
     const bool causal = S.causal != 0;
+    const bool cached = S.posterior_cached != 0;   // mu / var of an earlier sweep are still valid: EI refresh only
 
-    double* Lp = reinterpret_cast<double*>(smem_raw);  // packed lower triangle, row i at i(i+1)/2
-    double* al = Lp + (size_t)n * (n + 1) / 2;
-    double* sv = al + n;
-    double* xs = sv + n;                       // n x d
-    double* tcol = xs + (size_t)n * CBO_MAX_D;  // [n][kSweepThreads] forward-substitution workspace
+    SweepSmem sm;
+    sm.Lp = reinterpret_cast<double*>(smem_raw);
+    sm.al = sm.Lp + (size_t)n * (n + 1) / 2;
+    sm.sv = sm.al + n;
+    sm.xs = sm.sv + n;
+    sm.tcol = sm.xs + (size_t)n * CBO_MAX_D;
     __shared__ double red_v[kSweepThreads / 32];
     __shared__ long long red_i[kSweepThreads / 32];
     __shared__ int red_n[kSweepThreads / 32];
 
-    for (int e = tid; e < n * n; e += kSweepThreads) {
-        const int i = e / n, j = e % n;
-        if (j <= i) Lp[i * (i + 1) / 2 + j] = S.L[e];
+    if (!cached) {
+        for (int e = tid; e < n * n; e += kSweepThreads) {
+            const int i = e / n, j = e % n;
+            if (j <= i) sm.Lp[i * (i + 1) / 2 + j] = S.L[e];
+        }
+        for (int i = tid; i < n; i += kSweepThreads) {
+            sm.al[i] = S.alpha[i];
+            sm.sv[i] = causal ? S.sqrt_v_int[i] : 0.0;
+        }
+        for (int i = tid; i < n * d; i += kSweepThreads) sm.xs[i] = S.x_int[i];
+        __syncthreads();
     }
-    for (int i = tid; i < n; i += kSweepThreads) {
-        al[i] = S.alpha[i];
-        sv[i] = causal ? S.sqrt_v_int[i] : 0.0;
-    }
-    for (int i = tid; i < n * d; i += kSweepThreads) xs[i] = S.x_int[i];
-    __syncthreads();
 
     const long long loc = (long long)tile * kSweepThreads + tid;
     const bool valid = loc < S.g_count;
@@ -56,9 +116,25 @@ sweep_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, double best, d
     int is_nan = 0;
     if (valid) {
         double x[CBO_MAX_D];
-        if (S.points) {  // explicit candidates
+        const bool need_x = !cached || S.cost_variable;
+        if (!need_x) {
+#pragma unroll
+            for (int k = 0; k < CBO_MAX_D; ++k) x[k] = 0.0;
+        } else if (S.points) {  // explicit candidates
 #pragma unroll
             for (int k = 0; k < CBO_MAX_D; ++k) x[k] = k < d ? S.points[gidx * d + k] : 0.0;
+        } else if (S.g_total < 0x7fffffffLL) {  // 32-bit index arithmetic (64-bit div/mod is an emulated, long sequence)
+            unsigned gg = (unsigned)gidx;
+#pragma unroll
+            for (int k = CBO_MAX_D - 1; k >= 0; --k) {
+                if (k < d) {
+                    const unsigned pk = (unsigned)S.p[k], q = gg / pk;
+                    x[k] = S.grid[k][gg - q * pk];
+                    gg = q;
+                } else {
+                    x[k] = 0.0;
+                }
+            }
         } else {
             long long gg = gidx;
 #pragma unroll
@@ -72,30 +148,24 @@ sweep_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, double best, d
                 }
             }
         }
-        const double vg = causal ? S.v[loc] : 0.0;
-        const double mg = causal ? S.m[loc] : 0.0;
-        const double svg = causal ? sqrt(vg) : 0.0;
-        double mu = 0.0, ss = 0.0;
-        for (int i = 0; i < n; ++i) {
-            double r2 = 0.0;
-#pragma unroll
-            for (int k = 0; k < CBO_MAX_D; ++k) {
-                if (k < d) {
-                    const double t = x[k] - xs[i * d + k];
-                    r2 += t * t;
-                }
-            }
-            const double ks = exp(-0.5 * r2) + sv[i] * svg;
-            mu = fma(ks, al[i], mu);
-            const double* __restrict__ Li = Lp + i * (i + 1) / 2;
-            double a = ks;
-            for (int j = 0; j < i; ++j) a = fma(-Li[j], tcol[j * kSweepThreads + tid], a);
-            const double t = a / Li[i];
-            tcol[i * kSweepThreads + tid] = t;
-            ss = fma(t, t, ss);
+        double mu, var;
+        if (cached) {
+            mu = S.mu[loc];
+            var = S.var[loc];
+        } else {
+            const double vg = causal ? S.v[loc] : 0.0;
+            const double mg = causal ? S.m[loc] : 0.0;
+            const double svg = causal ? sqrt(vg) : 0.0;
+            double ss;
+            if (n <= 16) posterior_at<16>(sm, n, d, x, svg, tid, mu, ss);
+            else if (n <= 32) posterior_at<32>(sm, n, d, x, svg, tid, mu, ss);
+            else if (n <= 48) posterior_at<48>(sm, n, d, x, svg, tid, mu, ss);
+            else posterior_at<0>(sm, n, d, x, svg, tid, mu, ss);
+            mu += mg;
+            var = ((1.0 + vg) - ss) + 1e-10;
+            if (S.mu) S.mu[loc] = mu;
+            if (S.var) S.var[loc] = var;
         }
-        mu += mg;
-        const double var = ((1.0 + vg) - ss) + 1e-10;
         const double sd = sqrt(var);
         const double u = (best - mu) / sd;
         const double pdf = 0.3989422804014326779 * exp(-0.5 * u * u);
@@ -108,8 +178,6 @@ sweep_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, double best, d
                 if (k < d) cost += fabs(x[k]);
         }
         const double acq = ei / cost;
-        if (S.mu) S.mu[loc] = mu;
-        if (S.var) S.var[loc] = var;
         if (S.ei) S.ei[loc] = ei;
         if (S.acq) S.acq[loc] = acq;
         is_nan = acq != acq;
@@ -220,6 +288,7 @@ int sweep_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_s
         const cbo_set_desc& S = h_sets[s];
         CBO_REQUIRE(S.n_int >= 1 && S.n_int <= CBO_MAX_NINT, "cbo_sweep: set %d n_int=%d outside [1,%d]", s, S.n_int, CBO_MAX_NINT);
         CBO_REQUIRE(S.L && S.alpha && S.x_int, "cbo_sweep: set %d has a NULL posterior pointer", s);
+        CBO_REQUIRE(!S.posterior_cached || (S.mu && S.var), "cbo_sweep: set %d is marked posterior_cached without mu/var arrays", s);
         CBO_REQUIRE(!S.causal || (S.m && S.v && S.sqrt_v_int), "cbo_sweep: causal set %d needs m/v/sqrt_v_int", s);
         for (int k = 0; k < (S.points ? 0 : S.d); ++k) CBO_REQUIRE(S.grid[k], "cbo_sweep: set %d grid[%d] is NULL", s, k);
         total += host_items(S, kItemsSweep);
@@ -228,7 +297,7 @@ int sweep_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_s
     CBO_REQUIRE(total < 2147483647LL, "cbo_sweep: too many work items");
     if (total > 0) {
         const size_t smem = ((size_t)nmax * (nmax + 1) / 2 + 2 * (size_t)nmax + (size_t)nmax * CBO_MAX_D +
-                             (size_t)nmax * kSweepThreads) * sizeof(double);
+                             (nmax > 48 ? (size_t)nmax * kSweepThreads : 0)) * sizeof(double);
         static size_t configured = 0;
         if (smem > configured) {
             CBO_CUDA(cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

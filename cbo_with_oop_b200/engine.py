@@ -108,8 +108,10 @@ class SweepEngine:
         self.rank, self.world = rank, world_size
         self.group = process_group
         self.problems = list(problems)
-        self.keep = tuple(keep)
+        # mu / var are always kept: they are the cache behind the post-intervention EI refresh (refresh())
+        self.keep = tuple(dict.fromkeys(("mu", "var") + tuple(keep)))
         self.ncap = int(n_int_capacity)
+        self._posterior_valid = set()     # global ids whose mu / var arrays match their current interventional data
         self.timing = False
         self.launches = 0            # kernels of libcbo_b200 launched so far (bench.py reports the per-step count)
         self.pinned_staging = pinned_staging
@@ -309,6 +311,7 @@ class SweepEngine:
             off = li * C.sizeof(SetDesc)
             raw = bytearray(bytes(self.h_sets[li]))
             self.d_sets[off:off + len(raw)].copy_(torch.frombuffer(raw, dtype=torch.uint8))
+            self._posterior_valid.discard(g)
 
     # ------------------------------------------------------------------------------------------------
     @property
@@ -422,7 +425,20 @@ class SweepEngine:
         self._timed("posterior_fit", self.posterior_fit, ev)
         self._timed("prior_eval_grid", lambda: self.prior_eval(0), ev)
         self._timed("sweep", lambda: self._sweep_local(best, task), ev)
+        self._posterior_valid = set(self.active)
         return self._finish(ev)
+
+    def _mark_cached(self, cached_globals):
+        """Set posterior_cached on the given sets (and clear it on the others) in the host and device descriptors."""
+        changed = False
+        for li, g in enumerate(self.active):
+            flag = 1 if g in cached_globals else 0
+            if self.h_sets[li].posterior_cached != flag:
+                self.h_sets[li].posterior_cached = flag
+                changed = True
+        if changed:
+            raw = bytearray(bytes(self.h_sets))
+            self.d_sets.copy_(torch.frombuffer(raw, dtype=torch.uint8), non_blocking=False)
 
     def refresh(self, best: float, task: str = "min", refit: Sequence[int] = ()) -> SweepOutput:
         """Post-intervention trial: the prior on the grid is cached; only the sets in `refit` (global ids) get
@@ -437,7 +453,12 @@ class SweepEngine:
                 self._timed("tables", lambda: self.build_tables(li), ev)
                 self._timed("prior_eval_train", lambda: self.prior_eval(1, li), ev)
             self._timed("posterior_fit", lambda: self.posterior_fit(li), ev)
+        # sets that were not refitted keep their posterior: their share of the sweep is a 16 B/candidate EI refresh
+        cached = self._posterior_valid - set(refit)
+        self._mark_cached(cached)
         self._timed("sweep", lambda: self._sweep_local(best, task), ev)
+        self._mark_cached(set())
+        self._posterior_valid = set(self.active)
         return self._finish(ev)
 
     # ------------------------------------------------------------------------------------------------

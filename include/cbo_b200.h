@@ -30,7 +30,7 @@ extern "C" {
 #define CBO_API
 #endif
 
-#define CBO_ABI_VERSION 2
+#define CBO_ABI_VERSION 3
 #define CBO_MAX_D 4          /* intervened dimensions per exploration set (reference uses 1..3) */
 #define CBO_MAX_C 8          /* conditioning dimensions of an observational GP */
 #define CBO_MAX_NINT 128     /* interventional rows per set (reference: 10 .. ~50) */
@@ -97,6 +97,10 @@ typedef struct cbo_set_desc {
     double* ei;                /* optional: expected improvement */
     double* acq;               /* optional: ei / cost */
     /* ---- explicit candidates instead of a tensor grid (model.predict(X) / acquisition.evaluate(X) on arbitrary X) ---- */
+    int32_t posterior_cached;  /* 1: cbo_sweep reads this set's mu / var arrays (written by an earlier sweep with the same
+                                  interventional data) instead of recomputing them: the 16 B/candidate EI refresh of a
+                                  post-intervention trial for the sets that were not intervened on */
+    int32_t reserved1;
     const double* points;      /* NULL: tensor grid.  Otherwise (g_total, d) row-major candidates; then p[0] = g_total,
                                   p[1..] = 1, grid[] is unused and tab[0] is the (g_total, n_obs_pad) exp table of the points */
 } cbo_set_desc;
