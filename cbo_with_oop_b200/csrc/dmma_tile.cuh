@@ -44,18 +44,22 @@ __device__ __forceinline__ void load_rows_async(double* slab, const double* __re
 }
 
 // One pipeline stage of the warp-tiled product: warp (wm, wn) owns MA x NB blocks of 8x8.
-template <int BM, int BN, int MA, int NB>
+// LIVE = how many of the warp's MA row blocks hold live rows (compile time, so that dead blocks cost neither issue slots
+// nor pipe time -- predicated-off DMMAs still flow through the pipe).  LIVE == MA is the full tile; partially filled tiles
+// (the last tile of a grid slice, the few interventional rows) use the smaller instantiations.
+template <int BM, int BN, int MA, int NB, int LIVE = MA>
 __device__ __forceinline__ void mma_stage(const double* __restrict__ sA, const double* __restrict__ sB,
                                           double (&acc)[MA][NB][2], int row0, int col0, int lane) {
+    static_assert(LIVE >= 1 && LIVE <= MA, "LIVE row blocks");
 #pragma unroll
     for (int kb = 0; kb < kBK / 4; ++kb) {
-        double a[MA], b[NB];
+        double a[LIVE], b[NB];
 #pragma unroll
-        for (int mi = 0; mi < MA; ++mi) a[mi] = sA[((kb * BM + row0 + mi * 8) << 2) + lane];
+        for (int mi = 0; mi < LIVE; ++mi) a[mi] = sA[((kb * BM + row0 + mi * 8) << 2) + lane];
 #pragma unroll
         for (int ni = 0; ni < NB; ++ni) b[ni] = sB[((kb * BN + col0 + ni * 8) << 2) + lane];
 #pragma unroll
-        for (int mi = 0; mi < MA; ++mi)
+        for (int mi = 0; mi < LIVE; ++mi)
 #pragma unroll
             for (int ni = 0; ni < NB; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
     }

@@ -15,12 +15,14 @@
 //                           multiplies here -- and not inside the k loop -- matters: DMUL shares the FP64 pipe with
 //                           DMMA, and a producer warp issuing even 2 % of the pipe's work in the steady state stalled
 //                           on math-pipe throttle long enough to starve the consumers (77 % -> 96 % of DMMA peak).
-//   phase 2, producer     : one elected thread; per 16-deep stage two contiguous 16 KB TMA bulk copies
-//   (warp 8)                (cp.async.bulk, SASS UBLKCP): the M slab (K1a stores M blocked in fragment order) and
-//                           the U slab, both completing on the stage's "full" mbarrier (expect_tx = 32 KB).
-//   phase 2, consumers    : wait "full", 4 x (12 LDS.64 + 32 DMMA.8x8x4), arrive on "empty".  They never touch
-//   (warps 0-7)             global memory inside the k loop; after each J block a short epilogue dots the
-//                           accumulators with u (re-read from the scratch) and w.
+//   phase 2, producer     : one elected thread of a producer warpgroup (setmaxnreg 40); per 16-deep stage two contiguous
+//   (warps 8-11)            16 KB TMA bulk copies (cp.async.bulk, SASS UBLKCP): the M slab (K1a stores M blocked in
+//                           fragment order) and the U slab, both completing on the stage's "full" mbarrier (32 KB).
+//   phase 2, consumers    : (setmaxnreg 232) wait "full", 4 x (12 LDS.64 + 32 DMMA.8x8x4), arrive on "empty".  They
+//   (warps 0-7)             never touch global memory inside the k loop; after each J block a short epilogue dots the
+//                           accumulators with u (re-read from the scratch) and w.  Warps whose rows are partly or wholly
+//                           padding (interventional rows, last tile of a slice) run instantiations with 4 / 2 / 1 / 0
+//                           live row blocks.
 // Roofline: FP64 pipe.  Executed flops per candidate = N^2 (+ lower order); the dense-counted figure of
 // SURVEY.md §8(d) is 2 N^2 + 2 N + d N.  Scratch traffic: each U slab is re-read once per J block
 // (~N/256 times), about 1 TB/s of L2/HBM reads chip-wide at N = 1e4 -- 15 % of HBM bandwidth.
@@ -54,21 +56,133 @@ struct PriorCfg {
     static constexpr int WM = WM_, WN = WN_, MA = MA_, NB = NB_, STAGES = STAGES_;
     static constexpr int BM = WM * MA * 8;  // candidates per work item
     static constexpr int BN = WN * NB * 8;  // columns of M per J block
-    static constexpr int NCONS = WM * WN * 32, NT = NCONS + 32;  // + one producer warp
+    static constexpr int NCONS = WM * WN * 32;   // consumer warps first ...
+    static constexpr int NT = NCONS + 128;       // ... then one producer warpgroup (registers are allocated per warpgroup)
     static constexpr int A_TILE = BM * kBK;
     static constexpr int B_TILE = BN * kBK;
     static constexpr unsigned STAGE_BYTES = (A_TILE + B_TILE) * sizeof(double);
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 2 * WN * BM * sizeof(double) +
                                    (CBO_MAX_D + 1) * BM * sizeof(int32_t) + 2 * STAGES * sizeof(uint64_t) + 16;
+    // setmaxnreg redistributes the CTA's own allocation: NT x (registers per thread at launch, pinned by ptxas to the
+    // __launch_bounds__ ceiling).  Asking for more than the pool deadlocks the consumers on the inc.
+    static constexpr int LAUNCH_REGS = (65536 / NT) / 8 * 8;
+    static constexpr int PROD_REGS = 40, CONS_REGS = 232;
     static_assert(BM == CBO_PRIOR_TILE, "host item count assumes CBO_PRIOR_TILE points per work item");
     static_assert(BN == kMBlkRows, "the J block must match the row block of M's blocked layout");
+    static_assert(NCONS % 128 == 0, "setmaxnreg works on whole warpgroups");
+    static_assert(128 * PROD_REGS + NCONS * CONS_REGS <= NT * LAUNCH_REGS, "setmaxnreg budget exceeds the CTA's register pool");
 };
+
+// One decoded work item (everything both roles need); decoded redundantly by every thread from the descriptors.
+struct PriorItem {
+    const cbo_set_desc* S;
+    int tile, sp, ns, nJ;
+    __device__ __forceinline__ bool mine(int jb) const { const int r = jb % (2 * ns); return r == sp || r == 2 * ns - 1 - sp; }
+};
+
+__device__ __forceinline__ PriorItem decode_prior_item(const cbo_set_desc* __restrict__ sets, int num_sets, int which, int nsplit,
+                                                       int item) {
+    int local = item, s = 0;
+    for (; s < num_sets - 1; ++s) {
+        const int cnt = (int)prior_items(sets[s], which, nsplit);
+        if (local < cnt) break;
+        local -= cnt;
+    }
+    PriorItem it;
+    it.S = sets + s;
+    it.ns = prior_nsplit(sets[s], nsplit);
+    it.tile = local / it.ns;
+    it.sp = local % it.ns;
+    it.nJ = (sets[s].n_obs + kMBlkRows - 1) / kMBlkRows;
+    return it;
+}
+
+__device__ __forceinline__ void bar_all(int nthreads) { asm volatile("bar.sync 0, %0;" ::"r"(nthreads) : "memory"); }
+__device__ __forceinline__ void bar_consumers(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+
+// Consumer k loop + J-block epilogues of one work item for a warp whose first LIVE row blocks (of MA) hold live rows.
+// LIVE == 0: the warp owns only padding rows; it still walks the ring (wait full / arrive empty) so the counts match.
+template <class Cfg, int LIVE>
+__device__ __forceinline__ void consume_item(const PriorItem& it, const double* __restrict__ sA, const double* __restrict__ sB,
+                                             double* __restrict__ sRed, uint64_t* full, uint64_t* empty, int& stage, unsigned& phase,
+                                             const double* __restrict__ scratch, const double* __restrict__ w, int warp, int lane) {
+    constexpr int BM = Cfg::BM, BN = Cfg::BN, MA = Cfg::MA, NB = Cfg::NB, WN = Cfg::WN, STAGES = Cfg::STAGES;
+    constexpr int KB_PER_J = BN / kBK;
+    const int wm = warp / WN, wn = warp % WN;
+    const int row0 = wm * MA * 8, col0 = wn * NB * 8;
+    if constexpr (LIVE == 0) {
+#pragma unroll 1
+        for (int jb = 0; jb < it.nJ; ++jb) {
+            if (!it.mine(jb)) continue;
+#pragma unroll 1
+            for (int kt = 0; kt < (jb + 1) * KB_PER_J; ++kt) {
+                mbar_wait(&full[stage], phase);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+        return;
+    }
+    constexpr int LV = LIVE > 0 ? LIVE : 1;
+    double acc[MA][NB][2];
+#pragma unroll
+    for (int mi = 0; mi < MA; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NB; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+#pragma unroll 1
+    for (int jb = 0; jb < it.nJ; ++jb) {
+        if (!it.mine(jb)) continue;
+        const int nk = (jb + 1) * KB_PER_J, noff = jb * KB_PER_J;
+#pragma unroll 1
+        for (int kt = 0; kt < nk; ++kt) {
+            if (kt == noff) {  // strictly-lower blocks appear twice in u^T M u
+#pragma unroll
+                for (int mi = 0; mi < LV; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < NB; ++ni) { acc[mi][ni][0] *= 2.0; acc[mi][ni][1] *= 2.0; }
+            }
+            mbar_wait(&full[stage], phase);
+            mma_stage<BM, BN, MA, NB, LV>(sA + stage * Cfg::A_TILE, sB + stage * Cfg::B_TILE, acc, row0, col0, lane);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        // J-block epilogue: q_g += sum_{j in J} T[g][j] u[g][j] ; m_g += sum_{j in J} u[g][j] w[j]
+#pragma unroll
+        for (int mi = 0; mi < LV; ++mi) {
+            const int r = row0 + mi * 8 + (lane >> 2);
+            double q = 0.0, mm = 0.0;
+#pragma unroll
+            for (int ni = 0; ni < NB; ++ni) {
+                const int j = jb * BN + col0 + ni * 8 + (lane & 3) * 2;
+                const double2 u = __ldcg(reinterpret_cast<const double2*>(   // L2: never a stale L1 line of an earlier item
+                    scratch + (size_t)(j >> 4) * Cfg::A_TILE + frag_off(BM, (j & 15) >> 2, r, j & 3)));
+                const double2 ww = ldg_nc_d2(w + j);
+                q = fma(acc[mi][ni][0], u.x, q);
+                q = fma(acc[mi][ni][1], u.y, q);
+                mm = fma(u.x, ww.x, mm);
+                mm = fma(u.y, ww.y, mm);
+                acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+            }
+            q += __shfl_xor_sync(0xffffffffu, q, 1);
+            q += __shfl_xor_sync(0xffffffffu, q, 2);
+            mm += __shfl_xor_sync(0xffffffffu, mm, 1);
+            mm += __shfl_xor_sync(0xffffffffu, mm, 2);
+            if ((lane & 3) == 0) {  // (wn, r) has exactly one owner: no race, fixed order -> deterministic
+                sRed[wn * BM + r] += q;
+                sRed[(WN + wn) * BM + r] += mm;
+            }
+        }
+    }
+}
 
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::NT, 1)
 prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, int which, int nsplit, int total_items,
                   int* __restrict__ counter, double* __restrict__ partials, double* __restrict__ scratch_base, size_t slot_doubles) {
-    constexpr int BM = Cfg::BM, BN = Cfg::BN, MA = Cfg::MA, NB = Cfg::NB, WN = Cfg::WN, NT = Cfg::NT;
+    constexpr int BM = Cfg::BM, BN = Cfg::BN, WN = Cfg::WN, NT = Cfg::NT, NCONS = Cfg::NCONS;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int KB_PER_J = BN / kBK;
 
@@ -78,7 +192,7 @@ prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, int which
     double* sRed = sB + STAGES * Cfg::B_TILE;                          // [2][WN][BM] running q and m partial sums
     uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 2 * WN * BM);  // full[STAGES], empty[STAGES]
     int32_t* sRow = reinterpret_cast<int32_t*>(bars + 2 * STAGES);     // [CBO_MAX_D + 1][BM]: table row offsets, live flag
-    int32_t* sItem = sRow + (CBO_MAX_D + 1) * BM;
+    volatile int32_t* sItem = sRow + (CBO_MAX_D + 1) * BM;
     uint64_t* full = bars;
     uint64_t* empty = bars + STAGES;
 
@@ -91,105 +205,29 @@ prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, int which
             mbar_init(&empty[i], Cfg::WM * WN);  // one arrive per consumer warp
         }
         mbar_fence_init();
+        *sItem = atomicAdd(counter, 1);
     }
+    __syncthreads();
     int stage = 0;        // ring position, carried across work items (producer and consumers advance identically)
     unsigned phase = 0;
 
-    for (;;) {
-        __syncthreads();  // previous item fully retired (scratch, sRow, sRed reusable); barrier init visible
-        if (tid == 0) *sItem = atomicAdd(counter, 1);
-        __syncthreads();
-        const int item = *sItem;
-        if (item >= total_items) break;
-
-        // flat work item -> (set, tile, J split)
-        int local = item, s = 0;
-        for (; s < num_sets - 1; ++s) {
-            const int cnt = (int)prior_items(sets[s], which, nsplit);
-            if (local < cnt) break;
-            local -= cnt;
-        }
-        const cbo_set_desc& S = sets[s];
-        const int ns = prior_nsplit(S, nsplit);
-        const int tile = local / ns, sp = local % ns;
-        auto mine = [&](int jb) { const int r = jb % (2 * ns); return r == sp || r == 2 * ns - 1 - sp; };
-        // effective problem: the tensor grid (which == 0) or the n_int interventional rows (which == 1)
-        const int d = (which == 0 && !S.points) ? S.d : 1;  // explicit points and x_int use one row-per-point table
-        const long long gbeg = which == 0 ? S.g_begin : 0, gcnt = which == 0 ? S.g_count : S.n_int;
-        double* out_m = which == 0 ? S.m : S.m_int;
-        double* out_v = which == 0 ? S.v : S.v_int;
-        const int Npad = S.n_obs_pad;
-        const double* __restrict__ M = S.M;
-        const double* __restrict__ w = S.w;
-        const int nJ = (S.n_obs + BN - 1) / BN;
-        const int nKT = nJ * KB_PER_J;  // 16-wide column slabs of U that the k loop can touch
-
-        // per-row table offsets (C-order decomposition of the flat grid index, last dim fastest)
-        for (int r = tid; r < BM; r += NT) {
-            const long long loc = (long long)tile * BM + r;
-            const bool live = loc < gcnt;
-            long long gg = gbeg + (live ? loc : 0);
-#pragma unroll
-            for (int k = CBO_MAX_D - 1; k >= 0; --k) {
-                if (k < d) {
-                    const long long pk = which == 0 ? (S.points ? S.g_total : (long long)S.p[k]) : (long long)S.n_int;
-                    sRow[k * BM + r] = (int)(gg % pk) * Npad;
-                    gg /= pk;
-                }
-            }
-            sRow[CBO_MAX_D * BM + r] = live ? 1 : 0;
-        }
-        for (int i = tid; i < 2 * WN * BM; i += NT) sRed[i] = 0.0;
-        __syncthreads();
-
-        // ---- phase 1: U tile -> scratch, fragment order [kt][k4 group][row][4] -------------------------------
-        {
-            const double* tab[CBO_MAX_D];
-#pragma unroll
-            for (int k = 0; k < CBO_MAX_D; ++k) tab[k] = which == 0 ? S.tab[k < d ? k : 0] : S.u_int;
-            // unit = one 16-byte pair of one row; a warp's 32 units are 4 rows x 128 bytes of one slab: the table
-            // reads are four full lines and the scratch writes four full lines.
-            const int units = nKT * (BM * kBK / 2);
-            constexpr int UNROLL = 4;
-            for (int u0 = tid; u0 < units; u0 += NT * UNROLL) {
-                double2 v[UNROLL];
-                int dst[UNROLL];
-#pragma unroll
-                for (int x = 0; x < UNROLL; ++x) {
-                    const int u = u0 + x * NT;
-                    v[x] = make_double2(0.0, 0.0);
-                    dst[x] = -1;
-                    if (u < units) {
-                        const int kt = u >> 10, wi = u & 1023, l = wi & 31;
-                        const int kb = l >> 3, half = l & 1, row = (wi >> 5) * 4 + ((l & 7) >> 1);
-                        const int j = kt * kBK + kb * 4 + half * 2;
-                        dst[x] = kt * Cfg::A_TILE + frag_off(BM, kb, row, half * 2);
-                        if (sRow[CBO_MAX_D * BM + row]) {
-                            v[x] = ldg_nc_d2(tab[0] + sRow[row] + j);
-#pragma unroll
-                            for (int k = 1; k < CBO_MAX_D; ++k) {
-                                if (k < d) {
-                                    const double2 t = ldg_nc_d2(tab[k] + sRow[k * BM + row] + j);
-                                    v[x].x *= t.x; v[x].y *= t.y;
-                                }
-                            }
-                        }
-                    }
-                }
-#pragma unroll
-                for (int x = 0; x < UNROLL; ++x)
-                    if (dst[x] >= 0) *reinterpret_cast<double2*>(scratch + dst[x]) = v[x];
-            }
-            fence_proxy_async();  // generic-proxy writes above -> visible to the TMA (async proxy) reads below
-        }
-        __syncthreads();
-
-        if (warp == Cfg::WM * WN) {
-            // =============================== PRODUCER (one elected thread) ===============================
-            if (lane == 0) {
+    // Per item, three CTA-wide barriers (bar 0, all NT threads) in both roles:
+    //   A  the item id in sItem is valid                B  the U scratch of the item is complete (TMA may read it)
+    //   C  the item is retired (sItem / sRow / sRed / scratch may be overwritten)
+    if (warp >= NCONS / 32) {
+        // =============================== PRODUCER WARPGROUP (one elected thread works) ===============================
+        setmaxnreg_dec<Cfg::PROD_REGS>();
+        for (;;) {
+            const int item = *sItem;                                   // barrier A happened (kernel start / end of last item)
+            if (item >= total_items) break;
+            const PriorItem it = decode_prior_item(sets, num_sets, which, nsplit, item);
+            const double* __restrict__ M = it.S->M;
+            const int Npad = it.S->n_obs_pad;
+            bar_all(NT);                                               // B
+            if (warp == NCONS / 32 && lane == 0) {
 #pragma unroll 1
-                for (int jb = 0; jb < nJ; ++jb) {
-                    if (!mine(jb)) continue;
+                for (int jb = 0; jb < it.nJ; ++jb) {
+                    if (!it.mine(jb)) continue;
                     const int nk = (jb + 1) * KB_PER_J;
 #pragma unroll 1
                     for (int kt = 0; kt < nk; ++kt) {
@@ -201,78 +239,118 @@ prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, int which
                     }
                 }
             }
-            // the other lanes only need the ring position for the next item
-            stage = __shfl_sync(0xffffffffu, stage, 0);
-            phase = __shfl_sync(0xffffffffu, phase, 0);
-        } else {
-            // =============================== CONSUMERS ===============================
-            const int wm = warp / WN, wn = warp % WN;
-            const int row0 = wm * MA * 8, col0 = wn * NB * 8;
-            double acc[MA][NB][2];
-#pragma unroll
-            for (int mi = 0; mi < MA; ++mi)
-#pragma unroll
-                for (int ni = 0; ni < NB; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-
-#pragma unroll 1
-            for (int jb = 0; jb < nJ; ++jb) {
-                if (!mine(jb)) continue;
-                const int nk = (jb + 1) * KB_PER_J, noff = jb * KB_PER_J;
-#pragma unroll 1
-                for (int kt = 0; kt < nk; ++kt) {
-                    if (kt == noff) {  // strictly-lower blocks appear twice in u^T M u
-#pragma unroll
-                        for (int mi = 0; mi < MA; ++mi)
-#pragma unroll
-                            for (int ni = 0; ni < NB; ++ni) { acc[mi][ni][0] *= 2.0; acc[mi][ni][1] *= 2.0; }
-                    }
-                    mbar_wait(&full[stage], phase);
-                    mma_stage<BM, BN, MA, NB>(sA + stage * Cfg::A_TILE, sB + stage * Cfg::B_TILE, acc, row0, col0, lane);
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty[stage]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-                }
-                // J-block epilogue: q_g += sum_{j in J} T[g][j] u[g][j] ; m_g += sum_{j in J} u[g][j] w[j]
-#pragma unroll
-                for (int mi = 0; mi < MA; ++mi) {
-                    const int r = row0 + mi * 8 + (lane >> 2);
-                    double q = 0.0, mm = 0.0;
-#pragma unroll
-                    for (int ni = 0; ni < NB; ++ni) {
-                        const int j = jb * BN + col0 + ni * 8 + (lane & 3) * 2;
-                        const double2 u = __ldcg(reinterpret_cast<const double2*>(   // L2: never a stale L1 line of an earlier item
-                            scratch + (size_t)(j >> 4) * Cfg::A_TILE + frag_off(BM, (j & 15) >> 2, r, j & 3)));
-                        const double2 ww = ldg_nc_d2(w + j);
-                        q = fma(acc[mi][ni][0], u.x, q);
-                        q = fma(acc[mi][ni][1], u.y, q);
-                        mm = fma(u.x, ww.x, mm);
-                        mm = fma(u.y, ww.y, mm);
-                        acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-                    }
-                    q += __shfl_xor_sync(0xffffffffu, q, 1);
-                    q += __shfl_xor_sync(0xffffffffu, q, 2);
-                    mm += __shfl_xor_sync(0xffffffffu, mm, 1);
-                    mm += __shfl_xor_sync(0xffffffffu, mm, 2);
-                    if ((lane & 3) == 0) {  // (wn, r) has exactly one owner: no race, fixed order -> deterministic
-                        sRed[wn * BM + r] += q;
-                        sRed[(WN + wn) * BM + r] += mm;
-                    }
-                }
-            }
+            __syncwarp();
+            bar_all(NT);                                               // C (+ A of the next item: consumer thread 0 wrote sItem before it)
         }
-        __syncthreads();
-        for (int r = tid; r < BM; r += NT) {
-            const long long loc = (long long)tile * BM + r;
-            double qs = 0.0, ms = 0.0;
+    } else {
+        // =============================== CONSUMER WARPGROUPS ===============================
+        setmaxnreg_inc<Cfg::CONS_REGS>();
+        for (;;) {
+            const int item = *sItem;
+            if (item >= total_items) break;
+            const PriorItem it = decode_prior_item(sets, num_sets, which, nsplit, item);
+            const cbo_set_desc& S = *it.S;
+            // effective problem: the tensor grid (which == 0), explicit points, or the n_int interventional rows (which == 1)
+            const int d = (which == 0 && !S.points) ? S.d : 1;
+            const long long gbeg = which == 0 ? S.g_begin : 0, gcnt = which == 0 ? S.g_count : S.n_int;
+            const int Npad = S.n_obs_pad;
+            const int nKT = it.nJ * KB_PER_J;  // 16-wide column slabs of U that the k loop can touch
+            // live rows of this item (the last tile of a slice and the interventional rows fill only part of the 128):
+            // rows past them are never generated, multiplied or stored (rows of U are independent in U*M)
+            const long long left = gcnt - (long long)it.tile * BM;
+            const int nlive = left < BM ? (int)left : BM;
+
+            // per-row table offsets (C-order decomposition of the flat grid index, last dim fastest)
+            for (int r = tid; r < BM; r += NCONS) {
+                const bool live = r < nlive;
+                long long gg = gbeg + (live ? (long long)it.tile * BM + r : 0);
 #pragma unroll
-            for (int x = 0; x < WN; ++x) { qs += sRed[x * BM + r]; ms += sRed[(WN + x) * BM + r]; }
-            if (ns > 1) {              // partial sums of this J split; prior_finalize_kernel adds them up
-                partials[(size_t)item * kPartialDoubles + r] = qs;
-                partials[(size_t)item * kPartialDoubles + BM + r] = ms;
-            } else if (loc < gcnt) {
-                out_m[loc] = ms;
-                out_v[loc] = (S.s2 + S.noise) - qs;
+                for (int k = CBO_MAX_D - 1; k >= 0; --k) {
+                    if (k < d) {
+                        const long long pk = which == 0 ? (S.points ? S.g_total : (long long)S.p[k]) : (long long)S.n_int;
+                        sRow[k * BM + r] = (int)(gg % pk) * Npad;
+                        gg /= pk;
+                    }
+                }
+                sRow[CBO_MAX_D * BM + r] = live ? 1 : 0;
             }
+            for (int i = tid; i < 2 * WN * BM; i += NCONS) sRed[i] = 0.0;
+            bar_consumers(NCONS);
+
+            // ---- phase 1: U tile -> scratch, fragment order [kt][k4 group][row][4] -------------------------------
+            {
+                const double* tab[CBO_MAX_D];
+#pragma unroll
+                for (int k = 0; k < CBO_MAX_D; ++k) tab[k] = which == 0 ? S.tab[k < d ? k : 0] : S.u_int;
+                // unit = one 16-byte pair of one row; a warp's 32 units are 4 rows x 128 bytes of one slab: the table
+                // reads are four full lines and the scratch writes four full lines.
+                const int per_slab = ((nlive + 3) >> 2) * 32;   // 16-byte units of the live rows in one slab
+                const int units = nKT * per_slab;
+                constexpr int UNROLL = 4;
+                for (int u0 = tid; u0 < units; u0 += NCONS * UNROLL) {
+                    double2 v[UNROLL];
+                    int dst[UNROLL];
+#pragma unroll
+                    for (int x = 0; x < UNROLL; ++x) {
+                        const int u = u0 + x * NCONS;
+                        v[x] = make_double2(0.0, 0.0);
+                        dst[x] = -1;
+                        if (u < units) {
+                            const int kt = u / per_slab, wi = u - kt * per_slab, l = wi & 31;
+                            const int kb = l >> 3, half = l & 1, row = (wi >> 5) * 4 + ((l & 7) >> 1);
+                            const int j = kt * kBK + kb * 4 + half * 2;
+                            dst[x] = kt * Cfg::A_TILE + frag_off(BM, kb, row, half * 2);
+                            if (sRow[CBO_MAX_D * BM + row]) {
+                                v[x] = ldg_nc_d2(tab[0] + sRow[row] + j);
+#pragma unroll
+                                for (int k = 1; k < CBO_MAX_D; ++k) {
+                                    if (k < d) {
+                                        const double2 t = ldg_nc_d2(tab[k] + sRow[k * BM + row] + j);
+                                        v[x].x *= t.x; v[x].y *= t.y;
+                                    }
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int x = 0; x < UNROLL; ++x)
+                        if (dst[x] >= 0) *reinterpret_cast<double2*>(scratch + dst[x]) = v[x];
+                }
+                fence_proxy_async();  // generic-proxy writes above -> visible to the TMA (async proxy) reads below
+            }
+            bar_all(NT);                                               // B
+
+            {   // live row blocks of THIS warp (warp-uniform), rounded up to an instantiated count
+                const int live_here = nlive - (warp / WN) * Cfg::MA * 8;
+                const int need = live_here <= 0 ? 0 : (live_here + 7) >> 3;
+#define CBO_CONSUME(LIVE) consume_item<Cfg, LIVE>(it, sA, sB, sRed, full, empty, stage, phase, scratch, S.w, warp, lane)
+                if (need >= 5) CBO_CONSUME(8);
+                else if (need >= 3) CBO_CONSUME(4);
+                else if (need == 2) CBO_CONSUME(2);
+                else if (need == 1) CBO_CONSUME(1);
+                else CBO_CONSUME(0);
+#undef CBO_CONSUME
+            }
+            bar_consumers(NCONS);
+
+            double* out_m = which == 0 ? S.m : S.m_int;
+            double* out_v = which == 0 ? S.v : S.v_int;
+            for (int r = tid; r < nlive; r += NCONS) {
+                const long long loc = (long long)it.tile * BM + r;
+                double qs = 0.0, ms = 0.0;
+#pragma unroll
+                for (int x = 0; x < WN; ++x) { qs += sRed[x * BM + r]; ms += sRed[(WN + x) * BM + r]; }
+                if (it.ns > 1) {              // partial sums of this J split; prior_finalize_kernel adds them up
+                    partials[(size_t)item * kPartialDoubles + r] = qs;
+                    partials[(size_t)item * kPartialDoubles + BM + r] = ms;
+                } else {
+                    out_m[loc] = ms;
+                    out_v[loc] = (S.s2 + S.noise) - qs;
+                }
+            }
+            bar_consumers(NCONS);                                      // everyone has read this item's sItem / sRed
+            if (tid == 0) *sItem = atomicAdd(counter, 1);
+            bar_all(NT);                                               // C / A
         }
     }
 }
