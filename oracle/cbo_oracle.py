@@ -5,13 +5,19 @@ hot path (causal prior -> per-set GP posterior -> Expected Improvement / cost ->
 ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs may
 import it; the product (``cbo_with_oop_b200`` and ``src``) never does.
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for this path
- and its arithmetic lives in un-vendored third-party packages that are not installable
-here: GPy~=1.10.0, emukit~=0.4.10, paramz~=0.9.5 (reference requirements.txt:6-9).  The GPy internals
-restated below (``Stationary._scaled_dist``, ``ExactGaussianInference.inference``, ``jitchol``,
-``PosteriorExact._raw_predict``, ``Gaussian.predictive_values``) are their published algorithms; the
-plain-RBF GP is cross-checked against scikit-learn's GaussianProcessRegressor in
-tests/test_oracle.py so the oracle is not purely self-certified.
+PARITY STATUS.  The reference ships no tests, golden vectors or fixtures for this path, and its
+linear algebra lives in un-vendored third-party packages that are not installable here: GPy~=1.10.0,
+emukit~=0.4.10, paramz~=0.9.5 (reference requirements.txt:6-9).  What pins this oracle:
+  * PINNED against the reference's own code: tests/golden/reference_run_{toy,complete}.npz were produced by running
+    the reference's modules unmodified (DoCalculus.compute_do, CausalRBF.K/Kdiag, GaussianProcessFactory.create,
+    CausalExpectedImprovement, Cost, find_current_global, CBO.select_next_intervention) on the shipped data
+    (tests/golden/make_reference_golden.py); tests/test_reference_run.py holds this oracle to them (literal form 1e-8,
+    default form 1e-6, integers exact).
+  * UNPINNED: GPy's internals themselves.  In that run GPy/emukit/paramz were replaced by the stand-in under
+    tests/golden/gpy_standin, so ``Stationary._scaled_dist``, ``ExactGaussianInference.inference``, ``jitchol``,
+    ``PosteriorExact._raw_predict`` and ``Gaussian.predictive_values`` are restated from their published algorithms
+    (here and, independently, in the stand-in); the plain-RBF GP is cross-checked against scikit-learn's
+    GaussianProcessRegressor in tests/test_oracle.py so the restatement is not purely self-certified.
 
 Every function cites the reference file:line it follows (paths relative to /root/reference).
 """

@@ -80,3 +80,22 @@ def fit_errors(L, alpha, XI, yI, mI=None, vI=None, L_ref=None, alpha_ref=None):
 
 BACKWARD_TOL = 1e-12      # n * eps-level residuals of the Cholesky factor and of the two triangular solves
 MODERATE_COND = 1e6       # below this the forward errors of L and alpha must also meet RTOL
+
+
+def sweep_errors(got, exp, k=""):
+    """Errors of one exploration set's sweep arrays under the parity rule of DESIGN.md §2.
+    got / exp: mappings with mI, vI, mg, vg, mu, var, ei, acq (got at the same candidates as exp); exp keys carry prefix k."""
+    kd = 1.0 + exp[k + "vg"]
+    ei_scale = max(np.nanmax(np.abs(exp[k + "ei"])), 1e-300)
+    return {
+        "m_int": rel_err(got["mI"], exp[k + "mI"], 1e-6).max(),
+        "v_int": rel_err(got["vI"], exp[k + "vI"], 1e-6).max(),
+        "m": rel_err(got["mg"], exp[k + "mg"], 1e-6).max(),
+        "v": rel_err(got["vg"], exp[k + "vg"], 1e-6).max(),
+        # zero crossings of mu: relative to the larger of |mu| and 0.1 % of the set's range of mu (the solve behind mu
+        # has condition numbers up to 1e10 on the shipped data; both solvers are backward stable, see fit_errors)
+        "mu": rel_err(got["mu"], exp[k + "mu"], max(1e-4, 1e-3 * np.abs(exp[k + "mu"]).max())).max(),
+        "var": rel_err(got["var"], exp[k + "var"], 1e-4 * kd).max(),
+        "ei": np.nanmax(rel_err(got["ei"], exp[k + "ei"], 1e-6 * ei_scale)),
+        "acq": np.nanmax(rel_err(got["acq"], exp[k + "acq"], 1e-6 * ei_scale)),
+    }
