@@ -278,11 +278,13 @@ def run_ours(args, world, rank, local_rank):
         barrier()
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         nref = 5
-        for it in range(nref + 2):
+        x_cur, y_cur = x_old, y_old
+        for it in range(nref + 2):          # every trial appends one interventional row to the set, as CBO.intervene does
             if it == 2:
                 r0.record(torch.cuda.current_stream(dev))
-            x_new = np.vstack([x_old, rng.uniform(-2, 2, (1, D_INT))])
-            eng.set_interventional(g0, x_new, np.append(y_old, 0.0))
+            x_cur = np.vstack([x_cur, rng.uniform(-2, 2, (1, D_INT))])
+            y_cur = np.append(y_cur, 0.0)
+            eng.set_interventional(g0, x_cur, y_cur)
             out_r = eng.refresh(best, "min", refit=[g0])
         r1.record(torch.cuda.current_stream(dev))
         barrier()
@@ -292,8 +294,9 @@ def run_ours(args, world, rank, local_rank):
             dist.all_reduce(ms_r, op=dist.ReduceOp.MAX)
         refresh = {"ms_per_trial": float(ms_r.item()), "value": total_pts / (float(ms_r.item()) * 1e-3), "unit": UNIT,
                    "stage_ms": out_r.stage_ms,
-                   "what": "post-intervention trial: new interventional row -> interventional table, prior at x_int, refit of that "
-                           "set, full posterior + EI for it, EI refresh from cached mu/var (16 B/candidate) for the other sets, argmax"}
+                   "what": "post-intervention trial: one interventional row appended to a set -> its interventional table, the prior "
+                           "of the NEW row (u^T M u streams M once: HBM-bound), refit of that set, full posterior + EI for it, EI "
+                           "refresh from cached mu/var (16 B/candidate) for the other sets, argmax"}
 
     e2e_steps = max(1, min(args.e2e_steps, args.steps))
     ms_e, out_e, _, _, h2d = timed(e2e_steps, True)

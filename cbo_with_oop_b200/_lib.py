@@ -8,7 +8,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcbo_b200.so")
 
-CBO_ABI_VERSION = 3
+CBO_ABI_VERSION = 4
 CBO_MAX_D = 4
 CBO_MAX_C = 8
 CBO_MAX_NINT = 128
@@ -36,7 +36,7 @@ class SetDesc(C.Structure):
         ("L", _dp), ("alpha", _dp), ("sqrt_v_int", _dp), ("fit_info", _dp),
         ("cost_fix", C.c_double), ("cost_variable", C.c_int32), ("prior_external", C.c_int32),
         ("m", _dp), ("v", _dp), ("mu", _dp), ("var", _dp), ("ei", _dp), ("acq", _dp),
-        ("posterior_cached", C.c_int32), ("reserved1", C.c_int32),
+        ("posterior_cached", C.c_int32), ("int_row_begin", C.c_int32),
         ("points", _dp),
     ]
 
@@ -51,7 +51,7 @@ class SweepResult(C.Structure):
 
 EXPORTS = [
     "cbo_abi_version", "cbo_sizeof_set_desc", "cbo_offsetof_set_desc", "cbo_last_error", "cbo_sweep_num_items",
-    "cbo_prior_workspace_bytes",
+    "cbo_prior_workspace_bytes", "cbo_launch_count",
     "cbo_build_tables", "cbo_prior_precompute", "cbo_prior_eval", "cbo_posterior_fit", "cbo_sweep",
     "cbo_argmax_combine",
 ]
@@ -81,6 +81,7 @@ def load() -> C.CDLL:
     lib.cbo_offsetof_set_desc.restype = C.c_long
     lib.cbo_offsetof_set_desc.argtypes = [C.c_char_p]
     lib.cbo_last_error.restype = C.c_char_p
+    lib.cbo_launch_count.restype = C.c_ulonglong
     P = C.POINTER(SetDesc)
     lib.cbo_sweep_num_items.restype = C.c_long
     lib.cbo_sweep_num_items.argtypes = [P, C.c_int]
@@ -93,7 +94,7 @@ def load() -> C.CDLL:
     lib.cbo_sweep.argtypes = [P, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_void_p]
     lib.cbo_argmax_combine.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
-    for name in EXPORTS[6:]:
+    for name in EXPORTS[7:]:
         getattr(lib, name).restype = C.c_int
     if lib.cbo_abi_version() != CBO_ABI_VERSION:
         raise ImportError(f"ABI version mismatch: library {lib.cbo_abi_version()} != binding {CBO_ABI_VERSION}")

@@ -10,6 +10,10 @@
 namespace cbo {
 
 static thread_local char g_error[512] = "";
+static thread_local unsigned long long g_launches = 0;
+
+void note_launch(int n) { g_launches += (unsigned long long)n; }
+unsigned long long launch_count() { return g_launches; }
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -69,6 +73,7 @@ using namespace cbo;
 extern "C" {
 
 int cbo_abi_version(void) { return CBO_ABI_VERSION; }
+unsigned long long cbo_launch_count(void) { return launch_count(); }
 size_t cbo_sizeof_set_desc(void) { return sizeof(cbo_set_desc); }
 const char* cbo_last_error(void) { return g_error; }
 
@@ -78,7 +83,7 @@ long cbo_offsetof_set_desc(const char* field) {
     F(d) F(c) F(n_obs) F(n_obs_pad) F(n_mc) F(n_mc_pad) F(n_int) F(causal) F(p) F(g_total) F(g_begin) F(g_count)
     F(x_obs_int) F(x_obs_cond) F(mc_cond) F(alpha_obs) F(kyinv) F(ls_int) F(ls_cond) F(s2) F(noise)
     F(tab) F(u_int) F(P) F(pbar) F(w) F(M) F(grid) F(x_int) F(y_int) F(m_int) F(v_int) F(L) F(alpha) F(sqrt_v_int)
-    F(fit_info) F(cost_fix) F(cost_variable) F(prior_external) F(m) F(v) F(mu) F(var) F(ei) F(acq) F(posterior_cached) F(reserved1) F(points)
+    F(fit_info) F(cost_fix) F(cost_variable) F(prior_external) F(m) F(v) F(mu) F(var) F(ei) F(acq) F(posterior_cached) F(int_row_begin) F(points)
 #undef F
     return -1;
 }

@@ -29,6 +29,10 @@ int cuda_fail(cudaError_t e, const char* what);
 
 int validate_sets(const cbo_set_desc* h_sets, int num_sets);
 
+// Every kernel launch of the library is tallied per calling thread (cbo_launch_count): a diagnostic that lets the host
+// report how many of the library's kernels ran inside a timed region without re-deriving the launch logic.
+void note_launch(int n = 1);
+
 // does the library compute the causal prior of this set (as opposed to non-causal sets / caller-supplied priors)?
 __host__ __device__ inline bool computes_prior(const cbo_set_desc& S) { return S.causal && !S.prior_external; }
 

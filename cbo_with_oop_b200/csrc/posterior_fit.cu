@@ -137,6 +137,7 @@ int posterior_fit_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, i
         configured = smem;
     }
     posterior_fit_kernel<<<num_sets, kFitThreads, smem, st>>>(d_sets);
+    note_launch();
     CBO_CUDA(cudaGetLastError());
     return 0;
 }

@@ -21,7 +21,7 @@
 //   phase 2, consumers    : (setmaxnreg 232) wait "full", 4 x (12 LDS.64 + 32 DMMA.8x8x4), arrive on "empty".  They
 //   (warps 0-7)             never touch global memory inside the k loop; after each J block a short epilogue dots the
 //                           accumulators with u (re-read from the scratch) and w.  Warps whose rows are partly or wholly
-//                           padding (interventional rows, last tile of a slice) run instantiations with 4 / 2 / 1 / 0
+//                           padding (last tile of a slice, small explicit-point batches) run instantiations with fewer
 //                           live row blocks.
 // Roofline: FP64 pipe.  Executed flops per candidate = N^2 (+ lower order); the dense-counted figure of
 // SURVEY.md §8(d) is 2 N^2 + 2 N + d N.  Scratch traffic: each U slab is re-read once per J block
@@ -32,23 +32,45 @@ namespace cbo {
 
 constexpr int kPriorWsHeader = 256;  // bytes reserved at the start of the workspace (work counter)
 
-constexpr int kMaxSplit = 64;        // upper bound of the J split
 constexpr int kPartialDoubles = 2 * CBO_PRIOR_TILE;   // one (q, m) partial per row of a work item
+constexpr int kKbPerJ = kMBlkRows / kBK;              // 16-deep k slabs per 128-column block of M
+constexpr int kPartialFloor = 1024;                    // partial slots every workspace holds, besides 4 per CTA
 
-__host__ __device__ inline long long prior_tiles(const cbo_set_desc& S, int which) {
+// (this file is the grid / explicit-point evaluation, cbo_prior_eval which == 0; the interventional rows, which == 1,
+// are evaluated in compensated arithmetic by prior_rows.cu)
+__host__ __device__ inline long long prior_tiles(const cbo_set_desc& S) {
     if (!computes_prior(S)) return 0;
-    return ((which == 0 ? S.g_count : (long long)S.n_int) + CBO_PRIOR_TILE - 1) / CBO_PRIOR_TILE;
+    return (S.g_count + CBO_PRIOR_TILE - 1) / CBO_PRIOR_TILE;
 }
-// J split of one set: when a launch has too few 128-candidate tiles to fill the GPU (the interventional rows, small
-// grids) the column blocks of M are dealt to `ns` work items per tile, folded (jb mod 2ns in {sp, 2ns-1-sp}) so that the
-// triangular cost is balanced; the partial row sums are combined in a fixed order by prior_finalize_kernel.
+__host__ __device__ inline int prior_nJ(const cbo_set_desc& S) { return (S.n_obs + kMBlkRows - 1) / kMBlkRows; }
+
+// Work decomposition.  chunk == 0 (the grid): one item per 128-candidate tile walks every (jb, kt) of M's lower block
+// triangle.  chunk > 0 (too few tiles to fill the GPU: small grids, small explicit-point batches): the
+// triangle of each tile is cut into segments -- for column block jb, its strictly-lower k range in pieces of `chunk`
+// column blocks (ceil(jb / chunk) of them, each counted twice in u^T M u) and its diagonal block -- one item per segment,
+// so that M is streamed once by the WHOLE GPU and the launch is bound by HBM (or by the few rows' flops), not by one
+// SM per tile.  The per-item partial row sums are combined in item order by prior_finalize_kernel (deterministic).
+//   G(n) = sum_{x=0..n} ceil(x / chunk)   (closed form: decoding an item is O(sets) + O(log nJ))
+__host__ __device__ inline long long prior_G(int n, int chunk) {
+    if (n <= 0) return 0;
+    const long long q = n / chunk, r = n - q * chunk;
+    return (long long)chunk * q * (q + 1) / 2 + r * (q + 1);
+}
+// segments of column blocks [0, jb): F(jb) = sum_{x<jb} (ceil(x/chunk) + 1)
+__host__ __device__ inline long long prior_F(int jb, int chunk) { return prior_G(jb - 1, chunk) + jb; }
+// Fallback when a launch has too few tiles to fill the GPU but too many for segments to fit the partial buffer: the
+// column blocks are dealt to `ns` items per tile, folded (jb mod 2ns in {sp, 2ns-1-sp}) so the triangular cost balances.
 __host__ __device__ inline int prior_nsplit(const cbo_set_desc& S, int nsplit) {
-    const int nJ = (S.n_obs + kMBlkRows - 1) / kMBlkRows;
-    const int cap = nJ / 2 > 1 ? nJ / 2 : 1;
+    const int nJ = prior_nJ(S), cap = nJ / 2 > 1 ? nJ / 2 : 1;
     return nsplit < cap ? nsplit : cap;
 }
-__host__ __device__ inline long long prior_items(const cbo_set_desc& S, int which, int nsplit) {
-    return prior_tiles(S, which) * prior_nsplit(S, nsplit);
+// split = {chunk, nsplit}: chunk > 0 -> segments; else nsplit > 1 -> folded column blocks; else one item per tile
+struct PriorSplit { int chunk, nsplit; };
+__host__ __device__ inline long long prior_items_per_tile(const cbo_set_desc& S, PriorSplit sp) {
+    return sp.chunk > 0 ? prior_F(prior_nJ(S), sp.chunk) : prior_nsplit(S, sp.nsplit);
+}
+__host__ __device__ inline long long prior_items(const cbo_set_desc& S, PriorSplit sp) {
+    return prior_tiles(S) * prior_items_per_tile(S, sp);
 }
 
 template <int WM_, int WN_, int MA_, int NB_, int STAGES_>
@@ -74,26 +96,55 @@ struct PriorCfg {
 };
 
 // One decoded work item (everything both roles need); decoded redundantly by every thread from the descriptors.
+// It covers column blocks [jb0, jb1); a split item is one segment: a single column block and the k range [kt0, kt1)
+// (in 16-deep slabs), which lies either wholly below the diagonal block or is the diagonal block.
 struct PriorItem {
     const cbo_set_desc* S;
-    int tile, sp, ns, nJ;
+    int tile, nJ, jb0, jb1, kt0, kt1, sp, ns;
+    bool split;      // a segment item
+    bool partial;    // the item's row sums are partial (segments or folded column blocks): they go to the partial buffer
     __device__ __forceinline__ bool mine(int jb) const { const int r = jb % (2 * ns); return r == sp || r == 2 * ns - 1 - sp; }
+    __device__ __forceinline__ int kbeg(int jb) const { return split ? kt0 : 0; }
+    __device__ __forceinline__ int kend(int jb) const { return split ? kt1 : (jb + 1) * kKbPerJ; }
 };
 
-__device__ __forceinline__ PriorItem decode_prior_item(const cbo_set_desc* __restrict__ sets, int num_sets, int which, int nsplit,
-                                                       int item) {
+__device__ __forceinline__ PriorItem decode_prior_item(const cbo_set_desc* __restrict__ sets, int num_sets, PriorSplit split, int item) {
+    const int chunk = split.chunk;
     int local = item, s = 0;
     for (; s < num_sets - 1; ++s) {
-        const int cnt = (int)prior_items(sets[s], which, nsplit);
+        const int cnt = (int)prior_items(sets[s], split);
         if (local < cnt) break;
         local -= cnt;
     }
     PriorItem it;
     it.S = sets + s;
-    it.ns = prior_nsplit(sets[s], nsplit);
-    it.tile = local / it.ns;
-    it.sp = local % it.ns;
-    it.nJ = (sets[s].n_obs + kMBlkRows - 1) / kMBlkRows;
+    it.nJ = prior_nJ(sets[s]);
+    it.split = chunk > 0;
+    it.sp = 0, it.ns = 1;
+    if (!it.split) {
+        it.ns = prior_nsplit(sets[s], split.nsplit);
+        it.tile = local / it.ns, it.sp = local % it.ns;
+        it.jb0 = 0, it.jb1 = it.nJ, it.kt0 = it.kt1 = 0;
+        it.partial = it.ns > 1;
+        return it;
+    }
+    it.partial = prior_F(it.nJ, chunk) > 1;
+    const int per_tile = (int)prior_F(it.nJ, chunk);
+    it.tile = local / per_tile;
+    const int seg = local - it.tile * per_tile;
+    int lo = 0, hi = it.nJ - 1;                  // largest jb with F(jb) <= seg
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (prior_F(mid, chunk) <= seg) lo = mid; else hi = mid - 1;
+    }
+    const int jb = lo, piece = seg - (int)prior_F(jb, chunk), lower = (jb + chunk - 1) / chunk;
+    it.jb0 = jb, it.jb1 = jb + 1;
+    if (piece < lower) {                         // strictly-lower piece: column blocks [piece*chunk, min(jb, (piece+1)*chunk))
+        const int b1 = (piece + 1) * chunk < jb ? (piece + 1) * chunk : jb;
+        it.kt0 = piece * chunk * kKbPerJ, it.kt1 = b1 * kKbPerJ;
+    } else {                                     // the diagonal block
+        it.kt0 = jb * kKbPerJ, it.kt1 = (jb + 1) * kKbPerJ;
+    }
     return it;
 }
 
@@ -107,15 +158,15 @@ __device__ __forceinline__ void consume_item(const PriorItem& it, const double* 
                                              double* __restrict__ sRed, uint64_t* full, uint64_t* empty, int& stage, unsigned& phase,
                                              const double* __restrict__ scratch, const double* __restrict__ w, int warp, int lane) {
     constexpr int BM = Cfg::BM, BN = Cfg::BN, MA = Cfg::MA, NB = Cfg::NB, WN = Cfg::WN, STAGES = Cfg::STAGES;
-    constexpr int KB_PER_J = BN / kBK;
+    static_assert(BN / kBK == kKbPerJ, "J block width");
     const int wm = warp / WN, wn = warp % WN;
     const int row0 = wm * MA * 8, col0 = wn * NB * 8;
     if constexpr (LIVE == 0) {
 #pragma unroll 1
-        for (int jb = 0; jb < it.nJ; ++jb) {
+        for (int jb = it.jb0; jb < it.jb1; ++jb) {
             if (!it.mine(jb)) continue;
 #pragma unroll 1
-            for (int kt = 0; kt < (jb + 1) * KB_PER_J; ++kt) {
+            for (int kt = it.kbeg(jb); kt < it.kend(jb); ++kt) {
                 mbar_wait(&full[stage], phase);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[stage]);
@@ -132,24 +183,29 @@ __device__ __forceinline__ void consume_item(const PriorItem& it, const double* 
         for (int ni = 0; ni < NB; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
 #pragma unroll 1
-    for (int jb = 0; jb < it.nJ; ++jb) {
+    for (int jb = it.jb0; jb < it.jb1; ++jb) {
         if (!it.mine(jb)) continue;
-        const int nk = (jb + 1) * KB_PER_J, noff = jb * KB_PER_J;
+        const int kb = it.kbeg(jb), ke = it.kend(jb), noff = jb * kKbPerJ;   // noff: first slab of the diagonal block
+        auto double_acc = [&]() {   // strictly-lower blocks appear twice in u^T M u
+#pragma unroll
+            for (int mi = 0; mi < LV; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < NB; ++ni) { acc[mi][ni][0] *= 2.0; acc[mi][ni][1] *= 2.0; }
+        };
 #pragma unroll 1
-        for (int kt = 0; kt < nk; ++kt) {
-            if (kt == noff) {  // strictly-lower blocks appear twice in u^T M u
-#pragma unroll
-                for (int mi = 0; mi < LV; ++mi)
-#pragma unroll
-                    for (int ni = 0; ni < NB; ++ni) { acc[mi][ni][0] *= 2.0; acc[mi][ni][1] *= 2.0; }
-            }
+        for (int kt = kb; kt < ke; ++kt) {
+            if (kt == noff && kt != kb) double_acc();
             mbar_wait(&full[stage], phase);
             mma_stage<BM, BN, MA, NB, LV>(sA + stage * Cfg::A_TILE, sB + stage * Cfg::B_TILE, acc, row0, col0, lane);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
+        if (ke <= noff) double_acc();        // a split item's segment that lies wholly below the diagonal block
+        const bool with_m = ke > noff;        // the segment holding the diagonal block also carries the block's share of u.w
         // J-block epilogue: q_g += sum_{j in J} T[g][j] u[g][j] ; m_g += sum_{j in J} u[g][j] w[j]
+        // (u of column block jb sits in the scratch at slab jb*8 - ubase: a lower segment keeps it after its k slabs)
+        const int ubase = !it.split ? 0 : (ke <= noff ? noff - (ke - kb) : kb);
 #pragma unroll
         for (int mi = 0; mi < LV; ++mi) {
             const int r = row0 + mi * 8 + (lane >> 2);
@@ -158,12 +214,14 @@ __device__ __forceinline__ void consume_item(const PriorItem& it, const double* 
             for (int ni = 0; ni < NB; ++ni) {
                 const int j = jb * BN + col0 + ni * 8 + (lane & 3) * 2;
                 const double2 u = __ldcg(reinterpret_cast<const double2*>(   // L2: never a stale L1 line of an earlier item
-                    scratch + (size_t)(j >> 4) * Cfg::A_TILE + frag_off(BM, (j & 15) >> 2, r, j & 3)));
-                const double2 ww = ldg_nc_d2(w + j);
+                    scratch + (size_t)((j >> 4) - ubase) * Cfg::A_TILE + frag_off(BM, (j & 15) >> 2, r, j & 3)));
                 q = fma(acc[mi][ni][0], u.x, q);
                 q = fma(acc[mi][ni][1], u.y, q);
-                mm = fma(u.x, ww.x, mm);
-                mm = fma(u.y, ww.y, mm);
+                if (with_m) {
+                    const double2 ww = ldg_nc_d2(w + j);
+                    mm = fma(u.x, ww.x, mm);
+                    mm = fma(u.y, ww.y, mm);
+                }
                 acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
             }
             q += __shfl_xor_sync(0xffffffffu, q, 1);
@@ -180,12 +238,10 @@ __device__ __forceinline__ void consume_item(const PriorItem& it, const double* 
 
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::NT, 1)
-prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, int which, int nsplit, int total_items,
+prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, PriorSplit split, int total_items,
                   int* __restrict__ counter, double* __restrict__ partials, double* __restrict__ scratch_base, size_t slot_doubles) {
     constexpr int BM = Cfg::BM, BN = Cfg::BN, WN = Cfg::WN, NT = Cfg::NT, NCONS = Cfg::NCONS;
     constexpr int STAGES = Cfg::STAGES;
-    constexpr int KB_PER_J = BN / kBK;
-
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* sA = reinterpret_cast<double*>(smem_raw);
     double* sB = sA + STAGES * Cfg::A_TILE;
@@ -220,21 +276,21 @@ prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, int which
         for (;;) {
             const int item = *sItem;                                   // barrier A happened (kernel start / end of last item)
             if (item >= total_items) break;
-            const PriorItem it = decode_prior_item(sets, num_sets, which, nsplit, item);
+            const PriorItem it = decode_prior_item(sets, num_sets, split, item);
             const double* __restrict__ M = it.S->M;
             const int Npad = it.S->n_obs_pad;
             bar_all(NT);                                               // B
             if (warp == NCONS / 32 && lane == 0) {
 #pragma unroll 1
-                for (int jb = 0; jb < it.nJ; ++jb) {
+                for (int jb = it.jb0; jb < it.jb1; ++jb) {
                     if (!it.mine(jb)) continue;
-                    const int nk = (jb + 1) * KB_PER_J;
+                    const int kb = it.kbeg(jb), ke = it.kend(jb);
 #pragma unroll 1
-                    for (int kt = 0; kt < nk; ++kt) {
+                    for (int kt = kb; kt < ke; ++kt) {
                         mbar_wait(&empty[stage], phase ^ 1u);
                         mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
                         bulk_g2s(sB + stage * Cfg::B_TILE, M + mblk_base(jb, kt, Npad), Cfg::B_TILE * sizeof(double), &full[stage]);
-                        bulk_g2s(sA + stage * Cfg::A_TILE, scratch + (size_t)kt * Cfg::A_TILE, Cfg::A_TILE * sizeof(double), &full[stage]);
+                        bulk_g2s(sA + stage * Cfg::A_TILE, scratch + (size_t)(kt - kb) * Cfg::A_TILE, Cfg::A_TILE * sizeof(double), &full[stage]);
                         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                     }
                 }
@@ -248,13 +304,17 @@ prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, int which
         for (;;) {
             const int item = *sItem;
             if (item >= total_items) break;
-            const PriorItem it = decode_prior_item(sets, num_sets, which, nsplit, item);
+            const PriorItem it = decode_prior_item(sets, num_sets, split, item);
             const cbo_set_desc& S = *it.S;
-            // effective problem: the tensor grid (which == 0), explicit points, or the n_int interventional rows (which == 1)
-            const int d = (which == 0 && !S.points) ? S.d : 1;
-            const long long gbeg = which == 0 ? S.g_begin : 0, gcnt = which == 0 ? S.g_count : S.n_int;
+            // effective problem: the tensor grid, or explicit points (one table with a row per candidate)
+            const int d = S.points ? 1 : S.d;
+            const long long gbeg = S.g_begin, gcnt = S.g_count;
             const int Npad = S.n_obs_pad;
-            const int nKT = it.nJ * KB_PER_J;  // 16-wide column slabs of U that the k loop can touch
+            // 16-wide column slabs of U the item touches: all of them, or (split item) its k range [kt0, kt1) followed,
+            // for a segment below the diagonal, by the 8 slabs of column block jb that the epilogue dots with
+            const int nk_item = it.split ? it.kt1 - it.kt0 : it.nJ * kKbPerJ;
+            const bool extra = it.split && it.kt1 <= it.jb0 * kKbPerJ;
+            const int nKT = nk_item + (extra ? kKbPerJ : 0);
             // live rows of this item (the last tile of a slice and the interventional rows fill only part of the 128):
             // rows past them are never generated, multiplied or stored (rows of U are independent in U*M)
             const long long left = gcnt - (long long)it.tile * BM;
@@ -267,7 +327,7 @@ prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, int which
 #pragma unroll
                 for (int k = CBO_MAX_D - 1; k >= 0; --k) {
                     if (k < d) {
-                        const long long pk = which == 0 ? (S.points ? S.g_total : (long long)S.p[k]) : (long long)S.n_int;
+                        const long long pk = S.points ? S.g_total : (long long)S.p[k];
                         sRow[k * BM + r] = (int)(gg % pk) * Npad;
                         gg /= pk;
                     }
@@ -281,7 +341,7 @@ prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, int which
             {
                 const double* tab[CBO_MAX_D];
 #pragma unroll
-                for (int k = 0; k < CBO_MAX_D; ++k) tab[k] = which == 0 ? S.tab[k < d ? k : 0] : S.u_int;
+                for (int k = 0; k < CBO_MAX_D; ++k) tab[k] = S.tab[k < d ? k : 0];
                 // unit = one 16-byte pair of one row; a warp's 32 units are 4 rows x 128 bytes of one slab: the table
                 // reads are four full lines and the scratch writes four full lines.
                 const int per_slab = ((nlive + 3) >> 2) * 32;   // 16-byte units of the live rows in one slab
@@ -296,10 +356,11 @@ prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, int which
                         v[x] = make_double2(0.0, 0.0);
                         dst[x] = -1;
                         if (u < units) {
-                            const int kt = u / per_slab, wi = u - kt * per_slab, l = wi & 31;
+                            const int ks = u / per_slab, wi = u - ks * per_slab, l = wi & 31;   // ks: slab inside the scratch
                             const int kb = l >> 3, half = l & 1, row = (wi >> 5) * 4 + ((l & 7) >> 1);
+                            const int kt = !it.split ? ks : (ks < nk_item ? it.kt0 + ks : it.jb0 * kKbPerJ + (ks - nk_item));
                             const int j = kt * kBK + kb * 4 + half * 2;
-                            dst[x] = kt * Cfg::A_TILE + frag_off(BM, kb, row, half * 2);
+                            dst[x] = ks * Cfg::A_TILE + frag_off(BM, kb, row, half * 2);
                             if (sRow[CBO_MAX_D * BM + row]) {
                                 v[x] = ldg_nc_d2(tab[0] + sRow[row] + j);
 #pragma unroll
@@ -324,8 +385,11 @@ prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, int which
                 const int live_here = nlive - (warp / WN) * Cfg::MA * 8;
                 const int need = live_here <= 0 ? 0 : (live_here + 7) >> 3;
 #define CBO_CONSUME(LIVE) consume_item<Cfg, LIVE>(it, sA, sB, sRed, full, empty, stage, phase, scratch, S.w, warp, lane)
-                if (need >= 5) CBO_CONSUME(8);
-                else if (need >= 3) CBO_CONSUME(4);
+                if (need >= 7) CBO_CONSUME(8);
+                else if (need == 6) CBO_CONSUME(6);
+                else if (need == 5) CBO_CONSUME(5);
+                else if (need == 4) CBO_CONSUME(4);
+                else if (need == 3) CBO_CONSUME(3);
                 else if (need == 2) CBO_CONSUME(2);
                 else if (need == 1) CBO_CONSUME(1);
                 else CBO_CONSUME(0);
@@ -333,14 +397,14 @@ prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, int which
             }
             bar_consumers(NCONS);
 
-            double* out_m = which == 0 ? S.m : S.m_int;
-            double* out_v = which == 0 ? S.v : S.v_int;
+            double* out_m = S.m;
+            double* out_v = S.v;
             for (int r = tid; r < nlive; r += NCONS) {
                 const long long loc = (long long)it.tile * BM + r;
                 double qs = 0.0, ms = 0.0;
 #pragma unroll
                 for (int x = 0; x < WN; ++x) { qs += sRed[x * BM + r]; ms += sRed[(WN + x) * BM + r]; }
-                if (it.ns > 1) {              // partial sums of this J split; prior_finalize_kernel adds them up
+                if (it.partial) {             // partial sums of this segment / column-block share; prior_finalize_kernel adds them up
                     partials[(size_t)item * kPartialDoubles + r] = qs;
                     partials[(size_t)item * kPartialDoubles + BM + r] = ms;
                 } else {
@@ -355,25 +419,27 @@ prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, int which
     }
 }
 
-// Adds the J-split partials of every (set, tile) in split order (deterministic) and writes m, v.
+// Adds the partial row sums of every (set, tile) in item order (deterministic) and writes m, v.
 __global__ void __launch_bounds__(CBO_PRIOR_TILE)
-prior_finalize_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, int which, int nsplit,
+prior_finalize_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, PriorSplit split,
                       const double* __restrict__ partials) {
-    int base = 0;
+    long long base = 0;
     for (int s = 0; s < num_sets; ++s) {
         const cbo_set_desc& S = sets[s];
-        const int ns = prior_nsplit(S, nsplit), tiles = (int)prior_tiles(S, which);
-        if (ns > 1) {
-            const long long gcnt = which == 0 ? S.g_count : S.n_int;
-            double* out_m = which == 0 ? S.m : S.m_int;
-            double* out_v = which == 0 ? S.v : S.v_int;
+        const int tiles = (int)prior_tiles(S);
+        if (tiles == 0) continue;
+        const int per = (int)prior_items_per_tile(S, split);
+        if (per > 1) {
+            const long long gcnt = S.g_count;
+            double* out_m = S.m;
+            double* out_v = S.v;
             for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
                 const int r = threadIdx.x;
                 const long long loc = (long long)tile * CBO_PRIOR_TILE + r;
                 if (loc < gcnt) {
                     double qs = 0.0, ms = 0.0;
-                    for (int sp = 0; sp < ns; ++sp) {
-                        const double* p = partials + (size_t)(base + tile * ns + sp) * kPartialDoubles;
+                    const double* p = partials + (size_t)(base + (long long)tile * per) * kPartialDoubles;
+                    for (int i = 0; i < per; ++i, p += kPartialDoubles) {
                         qs += p[r];
                         ms += p[CBO_PRIOR_TILE + r];
                     }
@@ -382,7 +448,7 @@ prior_finalize_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, int w
                 }
             }
         }
-        base += tiles * ns;
+        base += (long long)tiles * per;
     }
 }
 
@@ -396,30 +462,38 @@ static size_t prior_slot_doubles(const cbo_set_desc* h_sets, int num_sets) {
     return (size_t)CBO_PRIOR_TILE * npad;
 }
 
-// workspace = [256 B header: work counter][partials: (4 ctas + 64) items][ctas scratch slots]
-static size_t prior_partial_items(long long ctas) { return (size_t)(4 * ctas + kMaxSplit); }
+static size_t prior_partial_items(long long ctas) { return (size_t)(4 * ctas + kPartialFloor); }
 
+size_t prior_rows_workspace_bytes(const cbo_set_desc* h_sets, int num_sets);
+int prior_rows_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_sets, void* d_ws, size_t ws_bytes,
+                    size_t ws_offset, cudaStream_t st);
+
+// workspace = [256 B header][partials][ctas scratch slots]; the interventional-rows kernel (which == 1, prior_rows.cu) runs
+// stream-ordered with the grid kernel and reuses everything behind the header for its own partials
 size_t prior_workspace_bytes_impl(const cbo_set_desc* h_sets, int num_sets, int num_ctas) {
-    return kPriorWsHeader + prior_partial_items(num_ctas) * kPartialDoubles * sizeof(double) +
-           (size_t)num_ctas * prior_slot_doubles(h_sets, num_sets) * sizeof(double);
+    const size_t grid = prior_partial_items(num_ctas) * kPartialDoubles * sizeof(double) +
+                        (size_t)num_ctas * prior_slot_doubles(h_sets, num_sets) * sizeof(double);
+    const size_t rows = prior_rows_workspace_bytes(h_sets, num_sets);
+    return kPriorWsHeader + (grid > rows ? grid : rows);
 }
 
 int prior_eval_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_sets, int which, void* d_ws,
                     size_t ws_bytes, cudaStream_t st) {
+    if (which == 1) return prior_rows_impl(h_sets, d_sets, num_sets, d_ws, ws_bytes, kPriorWsHeader, st);
     long long tiles = 0;
     for (int s = 0; s < num_sets; ++s) {
         const cbo_set_desc& S = h_sets[s];
         if (!computes_prior(S)) continue;
-        for (int k = 0; k < ((which == 0 && !S.points) ? S.d : 1); ++k) {
-            const long long pk = which == 0 ? (S.points ? S.g_total : (long long)S.p[k]) : (long long)S.n_int;
+        for (int k = 0; k < (S.points ? 1 : S.d); ++k) {
+            const long long pk = S.points ? S.g_total : (long long)S.p[k];
             CBO_REQUIRE(pk * (long long)S.n_obs_pad < 2147483647LL, "cbo_prior_eval: table %d of set %d too large", k, s);
         }
         CBO_REQUIRE((long long)CBO_PRIOR_TILE * S.n_obs_pad < 2147483647LL, "cbo_prior_eval: set %d n_obs_pad too large", s);
-        tiles += prior_tiles(S, which);
+        tiles += prior_tiles(S);
     }
     if (tiles == 0) return 0;
     const size_t slot = prior_slot_doubles(h_sets, num_sets);
-    const size_t fixed = kPriorWsHeader + (size_t)kMaxSplit * kPartialDoubles * sizeof(double);
+    const size_t fixed = kPriorWsHeader + (size_t)kPartialFloor * kPartialDoubles * sizeof(double);
     const size_t per_cta = 4 * kPartialDoubles * sizeof(double) + slot * sizeof(double);
     CBO_REQUIRE(d_ws != nullptr && ws_bytes >= fixed + per_cta,
                 "cbo_prior_eval: workspace of %zu bytes cannot hold one scratch slot (%zu bytes needed); see cbo_prior_workspace_bytes",
@@ -429,16 +503,30 @@ int prior_eval_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int 
     CBO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     long long ctas = (long long)((ws_bytes - fixed) / per_cta);
     if (ctas > sms) ctas = sms;      // one CTA per SM (shared memory bound); more slots than SMs are not used
-    // too few tiles to fill the GPU twice over: split the column blocks of M between work items
-    int nsplit = 1;
+    // too few tiles to fill the GPU twice over: cut every tile's triangle of M into segments (as fine as the partial
+    // buffer and a 4-items-per-CTA budget allow); when even the coarsest segments do not fit, deal out column blocks
+    PriorSplit split{0, 1};
+    auto count = [&](PriorSplit sp) {
+        long long t = 0;
+        for (int s = 0; s < num_sets; ++s) t += prior_items(h_sets[s], sp);
+        return t;
+    };
     if (tiles < 2 * ctas) {
-        nsplit = (int)((2 * ctas + tiles - 1) / tiles);
-        if (nsplit > kMaxSplit) nsplit = kMaxSplit;
+        int nJmax = 1;
+        for (int s = 0; s < num_sets; ++s)
+            if (prior_tiles(h_sets[s]) > 0 && prior_nJ(h_sets[s]) > nJmax) nJmax = prior_nJ(h_sets[s]);
+        const long long budget = (long long)prior_partial_items(ctas) < 4 * ctas ? (long long)prior_partial_items(ctas) : 4 * ctas;
+        for (int c = 1; c <= nJmax && nJmax > 1; ++c)
+            if (count(PriorSplit{c, 1}) <= budget) { split.chunk = c; break; }
+        if (split.chunk == 0) {
+            split.nsplit = (int)((2 * ctas + tiles - 1) / tiles);
+            while (split.nsplit > 1 && count(split) > (long long)prior_partial_items(ctas)) --split.nsplit;
+        }
     }
-    long long total = 0;
-    for (int s = 0; s < num_sets; ++s) total += prior_items(h_sets[s], which, nsplit);
+    const long long total = count(split);
+    const bool partial = split.chunk > 0 || split.nsplit > 1;
     CBO_REQUIRE(total < 2147483647LL, "cbo_prior_eval: too many work items");
-    CBO_REQUIRE(nsplit == 1 || (size_t)total <= prior_partial_items(ctas), "cbo_prior_eval: internal: partial buffer too small");
+    CBO_REQUIRE(!partial || (size_t)total <= prior_partial_items(ctas), "cbo_prior_eval: internal: partial buffer too small");
     const long long grid = ctas < total ? ctas : total;
     unsigned char* ws = reinterpret_cast<unsigned char*>(d_ws);
     double* partials = reinterpret_cast<double*>(ws + kPriorWsHeader);
@@ -450,11 +538,13 @@ int prior_eval_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int 
         configured = true;
     }
     CBO_CUDA(cudaMemsetAsync(d_ws, 0, kPriorWsHeader, st));
-    kern<<<(unsigned)grid, PriorCfgA::NT, PriorCfgA::SMEM, st>>>(d_sets, num_sets, which, nsplit, (int)total,
+    kern<<<(unsigned)grid, PriorCfgA::NT, PriorCfgA::SMEM, st>>>(d_sets, num_sets, split, (int)total,
                                                                  reinterpret_cast<int*>(ws), partials, scratch, slot);
+    note_launch();
     CBO_CUDA(cudaGetLastError());
-    if (nsplit > 1) {
-        prior_finalize_kernel<<<(unsigned)(tiles < 1024 ? tiles : 1024), CBO_PRIOR_TILE, 0, st>>>(d_sets, num_sets, which, nsplit, partials);
+    if (partial) {
+        prior_finalize_kernel<<<(unsigned)(tiles < 1024 ? tiles : 1024), CBO_PRIOR_TILE, 0, st>>>(d_sets, num_sets, split, partials);
+        note_launch();
         CBO_CUDA(cudaGetLastError());
     }
     return 0;

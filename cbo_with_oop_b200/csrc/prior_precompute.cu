@@ -168,6 +168,7 @@ int prior_precompute_impl(const cbo_set_desc* h_sets, int num_sets, cudaStream_t
         CBO_REQUIRE(S.kyinv && S.alpha_obs && S.M && S.w && S.pbar, "cbo_prior_precompute: set %d has a NULL pointer", s);
         if (S.c == 0) {
             nocond_kernel<<<dim3(8, S.n_obs_pad), 256, 0, st>>>(S.kyinv, S.alpha_obs, S.n_obs, S.n_obs_pad, S.s2, S.M, S.pbar, S.w);
+            note_launch();
             CBO_CUDA(cudaGetLastError());
             continue;
         }
@@ -176,10 +177,12 @@ int prior_precompute_impl(const cbo_set_desc* h_sets, int num_sets, cudaStream_t
         for (int k = 0; k < CBO_MAX_C; ++k) cp.il[k] = k < S.c ? 1.0 / S.ls_cond[k] : 0.0;
         pgen_kernel<<<S.n_obs_pad, 256, 0, st>>>(S.x_obs_cond, S.mc_cond, S.c, S.n_obs, S.n_mc, S.n_mc_pad, cp, S.alpha_obs,
                                                  S.s2, S.P, S.pbar, S.w);
+        note_launch();
         CBO_CUDA(cudaGetLastError());
         const int nT = S.n_obs_pad / CBO_NPAD;
         const int tiles = nT * (nT + 1) / 2;
         kern<<<tiles, 256, SMEM, st>>>(S.P, S.n_mc_pad, S.kyinv, S.n_obs, S.n_obs_pad, (S.s2 * S.s2) / (double)S.n_mc, S.M);
+        note_launch();
         CBO_CUDA(cudaGetLastError());
     }
     return 0;

@@ -304,11 +304,14 @@ int sweep_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_s
             configured = smem;
         }
         sweep_kernel<<<(unsigned)total, kSweepThreads, smem, st>>>(d_sets, num_sets, best, (double)task_sign, d_tile_best);
+        note_launch();
         CBO_CUDA(cudaGetLastError());
     }
     set_reduce_kernel<<<num_sets, 256, 0, st>>>(d_sets, num_sets, d_tile_best, d_set_best);
+    note_launch();
     CBO_CUDA(cudaGetLastError());
     combine_kernel<<<1, 128, 0, st>>>(nullptr, 0, num_sets, d_set_best, d_result);
+    note_launch();
     CBO_CUDA(cudaGetLastError());
     return 0;
 }
@@ -317,6 +320,7 @@ int argmax_combine_impl(const cbo_set_best* d_gathered, int num_ranks, int num_s
                         cbo_sweep_result* d_result, cudaStream_t st) {
     CBO_REQUIRE(d_gathered && num_ranks >= 1 && num_sets >= 1, "cbo_argmax_combine: bad arguments");
     combine_kernel<<<1, 128, 0, st>>>(d_gathered, num_ranks, num_sets, d_set_best, d_result);
+    note_launch();
     CBO_CUDA(cudaGetLastError());
     return 0;
 }

@@ -61,6 +61,7 @@ int build_tables_impl(const cbo_set_desc* h_sets, int num_sets, cudaStream_t st)
                 const unsigned gy = (unsigned)(S.g_total < 1024 ? S.g_total : 1024);
                 points_table_kernel<<<dim3(gx, gy), 256, 0, st>>>(S.points, (int)S.g_total, S.d, S.x_obs_int, S.n_obs, S.n_obs_pad,
                                                                   il[0], il[1], il[2], il[3], S.tab[0]);
+                note_launch();
             }
         }
         for (int k = 0; k < (S.points ? 0 : S.d); ++k) {
@@ -68,11 +69,13 @@ int build_tables_impl(const cbo_set_desc* h_sets, int num_sets, cudaStream_t st)
             const unsigned gy = (unsigned)(S.p[k] < 1024 ? S.p[k] : 1024);
             table_kernel<<<dim3(gx, gy), 256, 0, st>>>(S.grid[k], S.p[k], S.x_obs_int + (size_t)k * S.n_obs, S.n_obs,
                                                        S.n_obs_pad, 1.0 / S.ls_int[k], S.tab[k]);
+            note_launch();
         }
         CBO_REQUIRE(S.u_int && S.x_int, "cbo_build_tables: set %d has a NULL u_int/x_int pointer", s);
         const unsigned gy = (unsigned)(S.n_int < 1024 ? S.n_int : 1024);
         points_table_kernel<<<dim3(gx, gy), 256, 0, st>>>(S.x_int, S.n_int, S.d, S.x_obs_int, S.n_obs, S.n_obs_pad, il[0], il[1],
                                                           il[2], il[3], S.u_int);
+        note_launch();
         CBO_CUDA(cudaGetLastError());
     }
     return 0;

@@ -112,8 +112,10 @@ class SweepEngine:
         self.keep = tuple(dict.fromkeys(("mu", "var") + tuple(keep)))
         self.ncap = int(n_int_capacity)
         self._posterior_valid = set()     # global ids whose mu / var arrays match their current interventional data
+        self._prior_rows_valid = set()    # global ids whose m_int / v_int match the rows that were on the device last
+        self._row_begin = {}              # global id -> first interventional row without a prior yet (appended rows)
         self.timing = False
-        self.launches = 0            # kernels of libcbo_b200 launched so far (bench.py reports the per-step count)
+        self._launch0 = self.lib.cbo_launch_count()
         self.pinned_staging = pinned_staging
         for k in self.keep:
             if k not in ("mu", "var", "ei", "acq"):
@@ -125,6 +127,12 @@ class SweepEngine:
         self.local_of = {g: i for i, g in enumerate(self.active)}
         self._alloc()
         self.upload()
+
+    @property
+    def launches(self) -> int:
+        """Kernels of libcbo_b200 launched from this thread since the engine was built (the library tallies every
+        launch site itself: cbo_launch_count; bench.py reports the per-step difference)."""
+        return int(self.lib.cbo_launch_count() - self._launch0)
 
     # ------------------------------------------------------------------------------------------------
     def _dev(self, shape, dtype=torch.float64, zero=False):
@@ -299,12 +307,18 @@ class SweepEngine:
     def set_interventional(self, g: int, x_int: np.ndarray, y_int: np.ndarray):
         """Replace the interventional data of global set g (Monitor.add_intervention_data, Monitor.py:148-160)."""
         pr = self.problems[g]
+        old_x = pr.x_int
         pr.x_int = np.asarray(x_int, np.float64).reshape(-1, pr.d)
         pr.y_int = np.asarray(y_int, np.float64).reshape(-1)
         if pr.x_int.shape[0] > self.ncap:
             raise ValueError(f"set {g}: n_int={pr.x_int.shape[0]} exceeds capacity {self.ncap}")
         if g in self.local_of:
             li = self.local_of[g]
+            # rows appended to an unchanged prefix whose prior is on the device: the next refresh() evaluates the prior of
+            # the new rows only (cbo_set_desc.int_row_begin); anything else re-evaluates every row
+            n_old = old_x.shape[0]
+            appended = (g in self._prior_rows_valid and pr.x_int.shape[0] > n_old and np.array_equal(pr.x_int[:n_old], old_x))
+            self._row_begin[g] = min(self._row_begin.get(g, n_old), n_old) if appended else 0
             self.h_sets[li].n_int = pr.x_int.shape[0]
             self._h2d(self.buf[li]["x_int"], pr.x_int, (li, "x_int"), True)
             self._h2d(self.buf[li]["y_int"], pr.y_int, (li, "y_int"), True)
@@ -346,29 +360,22 @@ class SweepEngine:
         h, _, n = self._subset(local_ids)
         if n:
             _lib.check(self.lib.cbo_build_tables(h, n, self._stream()), "cbo_build_tables")
-            self.launches += sum(h[i].d + 1 for i in range(n) if h[i].causal and not h[i].prior_external)
 
     def prior_precompute(self, local_ids=None):
         h, _, n = self._subset(local_ids)
         if n:
             _lib.check(self.lib.cbo_prior_precompute(h, n, self._stream()), "cbo_prior_precompute")
-            self.launches += sum((2 if h[i].c > 0 else 1) for i in range(n) if h[i].causal and not h[i].prior_external)
 
     def prior_eval(self, which: int, local_ids=None):
         h, dptr, n = self._subset(local_ids)
         if n:
             _lib.check(self.lib.cbo_prior_eval(h, dptr, n, which, C.c_void_p(self.prior_ws.data_ptr()),
                                                self.prior_ws.numel(), self._stream()), "cbo_prior_eval")
-            act = [h[i] for i in range(n) if h[i].causal and not h[i].prior_external]
-            tiles = sum(-(-(a.g_count if which == 0 else a.n_int) // _lib.CBO_PRIOR_TILE) for a in act)
-            # one persistent kernel; plus the partial-sum finalize when the column blocks had to be split to fill the GPU
-            self.launches += (1 + (1 if tiles < 2 * self.num_sms else 0)) if tiles else 0
 
     def posterior_fit(self, local_ids=None):
         h, dptr, n = self._subset(local_ids)
         if n:
             _lib.check(self.lib.cbo_posterior_fit(h, dptr, n, self._stream()), "cbo_posterior_fit")
-            self.launches += 1
 
     def _sweep_local(self, best: float, task: str):
         A = len(self.active)
@@ -379,7 +386,6 @@ class SweepEngine:
                                           1 if task == "min" else -1, C.c_void_p(self.tile_best.data_ptr()),
                                           C.c_void_p(self.local_best.data_ptr()), C.c_void_p(self.result.data_ptr()),
                                           self._stream()), "cbo_sweep")
-            self.launches += 3
 
     def _finish(self, events) -> SweepOutput:
         """Scatter the local per-set bests into the global table, all-gather over ranks (NCCL), combine on
@@ -399,7 +405,6 @@ class SweepEngine:
             src, nr = gb, 1
         _lib.check(self.lib.cbo_argmax_combine(C.c_void_p(src.data_ptr()), nr, S, C.c_void_p(gb.data_ptr()),
                                                C.c_void_p(self.result.data_ptr()), self._stream()), "cbo_argmax_combine")
-        self.launches += 1
         res_h = self.result.cpu().numpy().tobytes()      # device -> host read of the step's result (synchronises)
         best_h = gb.cpu().numpy().tobytes()
         r = SweepResult.from_buffer_copy(res_h)
@@ -421,12 +426,26 @@ class SweepEngine:
         ev: list = []
         self._timed("tables", self.build_tables, ev)
         self._timed("prior_precompute", self.prior_precompute, ev)
+        self._set_row_begin({})
         self._timed("prior_eval_train", lambda: self.prior_eval(1), ev)
+        self._prior_rows_valid = {g for g in self.active if self.problems[g].computes_prior}
+        self._row_begin = {}
         self._timed("posterior_fit", self.posterior_fit, ev)
         self._timed("prior_eval_grid", lambda: self.prior_eval(0), ev)
         self._timed("sweep", lambda: self._sweep_local(best, task), ev)
         self._posterior_valid = set(self.active)
         return self._finish(ev)
+
+    def _set_row_begin(self, begins):
+        """Write int_row_begin (global id -> first row to evaluate; missing = 0) into the host and device descriptors."""
+        changed = False
+        for li, g in enumerate(self.active):
+            rb = int(begins.get(g, 0))
+            if self.h_sets[li].int_row_begin != rb:
+                self.h_sets[li].int_row_begin = rb
+                changed = True
+        if changed:
+            self.d_sets.copy_(torch.frombuffer(bytearray(bytes(self.h_sets)), dtype=torch.uint8), non_blocking=False)
 
     def _mark_cached(self, cached_globals):
         """Set posterior_cached on the given sets (and clear it on the others) in the host and device descriptors."""
@@ -445,6 +464,7 @@ class SweepEngine:
         their interventional table, prior at x_int and posterior refreshed
         (CBO.update_gaussian_process_of_last_intervention, CBO.py:224-235), then EI everywhere."""
         ev: list = []
+        self._set_row_begin({g: self._row_begin.get(g, 0) for g in refit if g in self._prior_rows_valid})
         for g in refit:
             if g not in self.local_of:
                 continue
@@ -452,7 +472,10 @@ class SweepEngine:
             if self.problems[g].computes_prior:
                 self._timed("tables", lambda: self.build_tables(li), ev)
                 self._timed("prior_eval_train", lambda: self.prior_eval(1, li), ev)
+                self._prior_rows_valid.add(g)
+                self._row_begin.pop(g, None)
             self._timed("posterior_fit", lambda: self.posterior_fit(li), ev)
+        self._set_row_begin({})
         # sets that were not refitted keep their posterior: their share of the sweep is a 16 B/candidate EI refresh
         cached = self._posterior_valid - set(refit)
         self._mark_cached(cached)
@@ -512,7 +535,6 @@ class SweepEngine:
                 _lib.check(self.lib.cbo_build_tables(h, 1, st), "cbo_build_tables")
                 _lib.check(self.lib.cbo_prior_eval(h, dptr, 1, 0, C.c_void_p(self.prior_ws.data_ptr()), self.prior_ws.numel(), st),
                            "cbo_prior_eval")
-                self.launches += 3
             if stages == "all":
                 n_items = self.lib.cbo_sweep_num_items(h, 1)
                 scratch = torch.empty(((n_items + 2) * C.sizeof(SetBest) + C.sizeof(SweepResult),), dtype=torch.uint8, device=dev)
@@ -520,7 +542,6 @@ class SweepEngine:
                 _lib.check(self.lib.cbo_sweep(h, dptr, 1, float(best), 1 if task == "min" else -1, C.c_void_p(base),
                                               C.c_void_p(base + n_items * C.sizeof(SetBest)),
                                               C.c_void_p(base + (n_items + 1) * C.sizeof(SetBest)), st), "cbo_sweep")
-                self.launches += 3
             for k in names:
                 out[k][a:a + mc] = bufs[k].cpu().numpy()
         return out

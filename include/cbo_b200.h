@@ -30,7 +30,7 @@ extern "C" {
 #define CBO_API
 #endif
 
-#define CBO_ABI_VERSION 3
+#define CBO_ABI_VERSION 4
 #define CBO_MAX_D 4          /* intervened dimensions per exploration set (reference uses 1..3) */
 #define CBO_MAX_C 8          /* conditioning dimensions of an observational GP */
 #define CBO_MAX_NINT 128     /* interventional rows per set (reference: 10 .. ~50) */
@@ -100,7 +100,9 @@ typedef struct cbo_set_desc {
     int32_t posterior_cached;  /* 1: cbo_sweep reads this set's mu / var arrays (written by an earlier sweep with the same
                                   interventional data) instead of recomputing them: the 16 B/candidate EI refresh of a
                                   post-intervention trial for the sets that were not intervened on */
-    int32_t reserved1;
+    int32_t int_row_begin;     /* cbo_prior_eval which=1 evaluates the interventional rows [int_row_begin, n_int) and leaves
+                                  m_int / v_int of the earlier rows untouched (a post-intervention trial appends one row);
+                                  0 = all rows */
     const double* points;      /* NULL: tensor grid.  Otherwise (g_total, d) row-major candidates; then p[0] = g_total,
                                   p[1..] = 1, grid[] is unused and tab[0] is the (g_total, n_obs_pad) exp table of the points */
 } cbo_set_desc;
@@ -125,6 +127,8 @@ CBO_API size_t cbo_sizeof_set_desc(void);
 /* Offset of a named field of cbo_set_desc, or -1: lets a foreign-language binding verify its mirror. */
 CBO_API long cbo_offsetof_set_desc(const char* field);
 CBO_API const char* cbo_last_error(void);
+/* Kernels launched by this library from the calling thread since it was loaded (diagnostic; bench.py's gpu_launches). */
+CBO_API unsigned long long cbo_launch_count(void);
 
 /* Number of sweep work items (tiles of CBO_SWEEP_TILE candidates) for this descriptor list; host-side
  * arithmetic only.  Callers size `d_tile_best` with it. */
@@ -141,13 +145,16 @@ CBO_API int cbo_build_tables(const cbo_set_desc* h_sets, int num_sets, void* str
 CBO_API int cbo_prior_precompute(const cbo_set_desc* h_sets, int num_sets, void* stream);
 
 /* K1b. causal prior m(x) = u.w, v(x) = s2 + noise - u^T M u.
- * which = 0: on the rank's slice of the tensor grid (writes m, v);
- * which = 1: on the interventional rows x_int (writes m_int, v_int).
+ * which = 0: on the rank's slice of the tensor grid, or on explicit points (writes m, v).  FP64 tensor pipe (DMMA);
+ *            persistent kernel, one CTA per SM; each CTA materialises the 128 x n_obs_pad table product of its current
+ *            128 candidates in a private slot of `d_workspace`.  Launches with too few 128-candidate tiles to fill the
+ *            GPU cut every tile's triangle of M into segments (deterministic partial sums).
+ * which = 1: on the interventional rows x_int[int_row_begin .. n_int) (writes m_int, v_int).  These values are the
+ *            inputs of the per-set fit, which amplifies their error by the Gram's condition number, so they are
+ *            accumulated in compensated (double-double) arithmetic; one pass over M, HBM-bound for a single appended row.
  * Replaces DoCalculus.update_do_function (DoCalculus.py:34-66), index 0 and 1 together.
- * The kernel is persistent (one CTA per SM); each CTA materialises the 128 x n_obs_pad table product of its
- * current 128 candidates in a private slot of `d_workspace` (device memory, 256-byte aligned).  Size it with
- * cbo_prior_workspace_bytes(h_sets, num_sets, num_ctas); num_ctas = the SM count uses the whole GPU, fewer slots
- * run fewer CTAs, at least one slot is required. */
+ * `d_workspace`: device memory, 256-byte aligned, sized with cbo_prior_workspace_bytes(h_sets, num_sets, num_ctas);
+ * num_ctas = the SM count uses the whole GPU, fewer slots run fewer CTAs, at least one slot is required. */
 CBO_API size_t cbo_prior_workspace_bytes(const cbo_set_desc* h_sets, int num_sets, int num_ctas);
 CBO_API int cbo_prior_eval(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_sets, int which,
                            void* d_workspace, size_t workspace_bytes, void* stream);

@@ -84,10 +84,21 @@ def run(config, experiment, n_obs, synthetic=False, max_keep=4096, store_kyinv=T
         ls = np.concatenate([pr.ls_int, pr.ls_cond])
         gp = dict(X=X, variance=pr.s2, lengthscale=ls, noise=pr.noise, alpha=pr.alpha_obs, Kyinv=pr.kyinv, form="diff")
         ref = O.sweep_set(gp, X, list(range(d)), pr.x_int, pr.y_int, pr.grid, best, "min", fix_costs=np.array([pr.cost_fix]),
-                          variable_cost=pr.cost_variable, causal=True, prior="factorised", form="diff")
+                          variable_cost=pr.cost_variable, causal=True, prior="factorised", form="diff", precise_int=True)
         G = pr.g_total
         stride = max(1, -(-G // max_keep))
         keep = np.arange(0, G, stride)
+        # every STORED value comes from the extended-precision prior (see do_prior_factorised): the interventional rows
+        # (above) and the kept candidates + the argmax (here); the full-grid pass that located the argmax is float64
+        pts = np.unique(np.append(keep, ref["idx"]))
+        Xp = np.stack([pr.grid[a][np.unravel_index(pts, [len(t) for t in pr.grid])[a]] for a in range(d)], 1)
+        mp, vp = O.do_prior_factorised(gp, ref["factors"], list(range(d)), Xp, precise=True)
+        mup, varp = O.posterior_predict(ref["post"], Xp, mp, vp)
+        eip = O.expected_improvement(mup, varp, best, "min")
+        acqp = eip / O.point_cost(Xp, np.array([pr.cost_fix]), pr.cost_variable)
+        for name, arr in (("mg", mp), ("vg", vp), ("mu", mup), ("var", varp), ("ei", eip), ("acq", acqp)):
+            ref[name] = np.array(ref[name]); ref[name][pts] = arr
+        ref["val"] = float(ref["acq"][ref["idx"]])
         k = f"set{s}_"
         # Ky^-1 (N x N per set) dominates the file size: the coral configs store the GP's training targets instead and
         # the test rebuilds (alpha, Ky^-1) with cbo_with_oop_b200.obs_gp.fit_state (deterministic LAPACK, agrees to ~1e-13)

@@ -85,7 +85,7 @@ def test_golden_config(cuda_engine_ready, config, expected):
         errs["alpha"] = fe["alpha_forward"] if fe["cond"] < MODERATE_COND else 0.0
         for name, e in errs.items():
             worst[name] = max(worst.get(name, 0.0), float(e))
-            assert e <= RTOL, f"{config} set {s} ({z[k + 'name']}) {name}: {e:.3e}"
+            assert e <= RTOL, f"{config} set {s} ({z[k + 'name']}) {name}: {e:.3e}; cond {fe['cond']:.2e}; all {errs}"
         # bit-exact selection -- unless the oracle's own top two candidates tie to rounding (flat acquisition far from
         # every interventional row): then any member of the tie set is a correct argmax and the GPU's pick must be one
         gap = float(z[k + "top2_gap"])

@@ -149,6 +149,25 @@ def test_refresh_after_intervention(cuda_engine_ready):
     refs = [oracle_sweep(ora2 if i == g else cases[i][1], best - 0.3, "min") for i in range(2)]
     np.testing.assert_allclose(out_r.set_values, [r["val"] for r in refs], rtol=RTOL)
     np.testing.assert_array_equal(out_r.set_indices, [r["idx"] for r in refs])
+    # the appended row alone was evaluated (cbo_set_desc.int_row_begin); the earlier rows kept their prior bit for bit
+    m_first = eng.fetch("m_int", g)
+    np.testing.assert_allclose(m_first, refs[g]["mI"], rtol=RTOL)
+    # a second appended row, then a rewritten row (no longer an append: every row is re-evaluated)
+    lo = np.array([t[0] for t in kw["grid"]]); hi = np.array([t[-1] for t in kw["grid"]])
+    x3 = np.vstack([x_new, (0.25 * lo + 0.75 * hi)[None, :]])
+    y3 = np.append(y_new, best + 0.1)
+    eng.set_interventional(g, x3, y3)
+    out3 = eng.refresh(best - 0.3, "min", refit=[g])
+    np.testing.assert_array_equal(eng.fetch("m_int", g)[:len(m_first)], m_first)
+    x4 = x3.copy(); x4[1] = 0.5 * (lo + hi) + 0.01
+    eng.set_interventional(g, x4, y3)
+    out4 = eng.refresh(best - 0.3, "min", refit=[g])
+    for xx, oo in ((x3, out3), (x4, out4)):
+        refs = [oracle_sweep(dict(ora, XI=xx, yI=y3) if i == g else cases[i][1], best - 0.3, "min") for i in range(2)]
+        np.testing.assert_allclose(oo.set_values, [r["val"] for r in refs], rtol=RTOL)
+        np.testing.assert_array_equal(oo.set_indices, [r["idx"] for r in refs])
+    np.testing.assert_allclose(eng.fetch("m_int", g), refs[g]["mI"], rtol=RTOL)
+    np.testing.assert_allclose(eng.fetch("v_int", g), refs[g]["vI"], rtol=RTOL)
 
 
 def test_jitter_retry_and_nan_policy(cuda_engine_ready):
