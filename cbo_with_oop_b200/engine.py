@@ -199,9 +199,11 @@ class SweepEngine:
         self.prior_ws = torch.empty((max(ws, 256),), dtype=torch.uint8, device=self.device)
         self.tile_best = torch.empty((max(n_items, 1) * C.sizeof(SetBest),), dtype=torch.uint8, device=self.device)
         self.local_best = torch.empty((max(A, 1) * C.sizeof(SetBest),), dtype=torch.uint8, device=self.device)
-        self.result = torch.empty((C.sizeof(SweepResult),), dtype=torch.uint8, device=self.device)
         S = len(self.problems)
-        self.global_best = torch.empty((S * C.sizeof(SetBest),), dtype=torch.uint8, device=self.device)
+        # [cbo_sweep_result | S x cbo_set_best]: the step's whole result, read back with ONE device -> host copy
+        self.out_buf = torch.empty((C.sizeof(SweepResult) + S * C.sizeof(SetBest),), dtype=torch.uint8, device=self.device)
+        self.result = self.out_buf[:C.sizeof(SweepResult)]
+        self.global_best = self.out_buf[C.sizeof(SweepResult):]
         self.gathered = torch.empty((self.world * S * C.sizeof(SetBest),), dtype=torch.uint8, device=self.device)
         empty = (SetBest * S)()
         for s in range(S):
@@ -250,8 +252,17 @@ class SweepEngine:
                 D.u_int, D.pbar, D.w, D.M = ptr("u_int"), ptr("pbar"), ptr("w"), ptr("M")
                 D.P = self.P.data_ptr() if (self.P is not None and c > 0) else None
         A = len(self.active)
-        raw = bytearray(bytes(self.h_sets)) if A else bytearray(C.sizeof(SetDesc))
-        self.d_sets = torch.frombuffer(raw, dtype=torch.uint8).to(self.device)
+        self.d_sets = torch.empty((max(A, 1) * C.sizeof(SetDesc),), dtype=torch.uint8, device=self.device)
+        self._descs_dirty = True
+        self._push_descs()
+
+    def _push_descs(self):
+        """Upload the host descriptor array if it changed since the last upload.  Flag and size changes only touch the
+        host copy; every stage call starts with this, so a trial uploads the descriptors once, not once per change."""
+        if self._descs_dirty:
+            raw = bytearray(bytes(self.h_sets))
+            self.d_sets.copy_(torch.frombuffer(raw, dtype=torch.uint8))
+            self._descs_dirty = False
 
     # ------------------------------------------------------------------------------------------------
     def _h2d(self, dst: torch.Tensor, arr: np.ndarray, key, restage: bool):
@@ -322,9 +333,7 @@ class SweepEngine:
             self.h_sets[li].n_int = pr.x_int.shape[0]
             self._h2d(self.buf[li]["x_int"], pr.x_int, (li, "x_int"), True)
             self._h2d(self.buf[li]["y_int"], pr.y_int, (li, "y_int"), True)
-            off = li * C.sizeof(SetDesc)
-            raw = bytearray(bytes(self.h_sets[li]))
-            self.d_sets[off:off + len(raw)].copy_(torch.frombuffer(raw, dtype=torch.uint8))
+            self._descs_dirty = True
             self._posterior_valid.discard(g)
 
     # ------------------------------------------------------------------------------------------------
@@ -337,6 +346,7 @@ class SweepEngine:
 
     def _subset(self, local_ids: Optional[Sequence[int]]):
         """(host descriptor pointer, device descriptor pointer, count) for all active sets or a contiguous run."""
+        self._push_descs()
         A = len(self.active)
         if local_ids is None:
             return self.h_sets, C.c_void_p(self.d_sets.data_ptr()), A
@@ -381,6 +391,7 @@ class SweepEngine:
         A = len(self.active)
         if task not in ("min", "max"):
             raise ValueError("task must be 'min' or 'max'")
+        self._push_descs()
         if A:
             _lib.check(self.lib.cbo_sweep(self.h_sets, C.c_void_p(self.d_sets.data_ptr()), A, float(best),
                                           1 if task == "min" else -1, C.c_void_p(self.tile_best.data_ptr()),
@@ -405,8 +416,8 @@ class SweepEngine:
             src, nr = gb, 1
         _lib.check(self.lib.cbo_argmax_combine(C.c_void_p(src.data_ptr()), nr, S, C.c_void_p(gb.data_ptr()),
                                                C.c_void_p(self.result.data_ptr()), self._stream()), "cbo_argmax_combine")
-        res_h = self.result.cpu().numpy().tobytes()      # device -> host read of the step's result (synchronises)
-        best_h = gb.cpu().numpy().tobytes()
+        out_h = self.out_buf.cpu().numpy().tobytes()     # ONE device -> host read of the step's result (synchronises)
+        res_h, best_h = out_h[:C.sizeof(SweepResult)], out_h[C.sizeof(SweepResult):]
         r = SweepResult.from_buffer_copy(res_h)
         bests = (SetBest * S).from_buffer_copy(best_h)
         x = None
@@ -437,34 +448,34 @@ class SweepEngine:
         return self._finish(ev)
 
     def _set_row_begin(self, begins):
-        """Write int_row_begin (global id -> first row to evaluate; missing = 0) into the host and device descriptors."""
+        """Write int_row_begin (global id -> first row to evaluate; missing = 0) into the host descriptors."""
         changed = False
         for li, g in enumerate(self.active):
             rb = int(begins.get(g, 0))
             if self.h_sets[li].int_row_begin != rb:
                 self.h_sets[li].int_row_begin = rb
                 changed = True
-        if changed:
-            self.d_sets.copy_(torch.frombuffer(bytearray(bytes(self.h_sets)), dtype=torch.uint8), non_blocking=False)
+        self._descs_dirty |= changed
 
     def _mark_cached(self, cached_globals):
-        """Set posterior_cached on the given sets (and clear it on the others) in the host and device descriptors."""
+        """Set posterior_cached on the given sets (and clear it on the others) in the host descriptors."""
         changed = False
         for li, g in enumerate(self.active):
             flag = 1 if g in cached_globals else 0
             if self.h_sets[li].posterior_cached != flag:
                 self.h_sets[li].posterior_cached = flag
                 changed = True
-        if changed:
-            raw = bytearray(bytes(self.h_sets))
-            self.d_sets.copy_(torch.frombuffer(raw, dtype=torch.uint8), non_blocking=False)
+        self._descs_dirty |= changed
 
     def refresh(self, best: float, task: str = "min", refit: Sequence[int] = ()) -> SweepOutput:
         """Post-intervention trial: the prior on the grid is cached; only the sets in `refit` (global ids) get
         their interventional table, prior at x_int and posterior refreshed
         (CBO.update_gaussian_process_of_last_intervention, CBO.py:224-235), then EI everywhere."""
         ev: list = []
+        # sets that are not refitted keep their posterior: their share of the sweep is a 16 B/candidate EI refresh.
+        # Both flags go into the descriptors before the first kernel: one upload for the whole trial.
         self._set_row_begin({g: self._row_begin.get(g, 0) for g in refit if g in self._prior_rows_valid})
+        self._mark_cached(self._posterior_valid - set(refit))
         for g in refit:
             if g not in self.local_of:
                 continue
@@ -475,11 +486,8 @@ class SweepEngine:
                 self._prior_rows_valid.add(g)
                 self._row_begin.pop(g, None)
             self._timed("posterior_fit", lambda: self.posterior_fit(li), ev)
-        self._set_row_begin({})
-        # sets that were not refitted keep their posterior: their share of the sweep is a 16 B/candidate EI refresh
-        cached = self._posterior_valid - set(refit)
-        self._mark_cached(cached)
         self._timed("sweep", lambda: self._sweep_local(best, task), ev)
+        self._set_row_begin({})      # host flags back to neutral; the device copy follows with the next trial's upload
         self._mark_cached(set())
         self._posterior_valid = set(self.active)
         return self._finish(ev)
