@@ -65,6 +65,8 @@ int posterior_fit_impl(const cbo_set_desc*, const cbo_set_desc*, int, cudaStream
 int sweep_impl(const cbo_set_desc*, const cbo_set_desc*, int, double, int, cbo_set_best*, cbo_set_best*, cbo_sweep_result*,
                cudaStream_t);
 int argmax_combine_impl(const cbo_set_best*, int, int, cbo_set_best*, cbo_sweep_result*, cudaStream_t);
+size_t obs_gp_workspace_bytes_impl(const cbo_set_desc*, int);
+int obs_gp_fit_impl(const cbo_set_desc*, int, double, void*, size_t, int32_t*, cudaStream_t);
 
 }  // namespace cbo
 
@@ -83,7 +85,7 @@ long cbo_offsetof_set_desc(const char* field) {
     F(d) F(c) F(n_obs) F(n_obs_pad) F(n_mc) F(n_mc_pad) F(n_int) F(causal) F(p) F(g_total) F(g_begin) F(g_count)
     F(x_obs_int) F(x_obs_cond) F(mc_cond) F(alpha_obs) F(kyinv) F(ls_int) F(ls_cond) F(s2) F(noise)
     F(tab) F(u_int) F(P) F(pbar) F(w) F(M) F(grid) F(x_int) F(y_int) F(m_int) F(v_int) F(L) F(alpha) F(sqrt_v_int)
-    F(fit_info) F(cost_fix) F(cost_variable) F(prior_external) F(m) F(v) F(mu) F(var) F(ei) F(acq) F(posterior_cached) F(int_row_begin) F(points)
+    F(fit_info) F(cost_fix) F(cost_variable) F(prior_external) F(m) F(v) F(mu) F(var) F(ei) F(acq) F(posterior_cached) F(int_row_begin) F(y_obs) F(points)
 #undef F
     return -1;
 }
@@ -93,6 +95,18 @@ long cbo_sweep_num_items(const cbo_set_desc* h_sets, int num_sets) {
     long long t = 0;
     for (int s = 0; s < num_sets; ++s) t += host_items(h_sets[s], kItemsSweep);
     return (long)t;
+}
+
+size_t cbo_obs_gp_workspace_bytes(const cbo_set_desc* h_sets, int num_sets) {
+    if (!h_sets || num_sets < 1) return 0;
+    return obs_gp_workspace_bytes_impl(h_sets, num_sets);
+}
+
+int cbo_obs_gp_fit(const cbo_set_desc* h_sets, int num_sets, double jitter, void* d_workspace, size_t workspace_bytes,
+                   int32_t* d_info, void* stream) {
+    if (int rc = validate_sets(h_sets, num_sets)) return rc;
+    CBO_REQUIRE(jitter >= 0.0, "cbo_obs_gp_fit: jitter must be non-negative");
+    return obs_gp_fit_impl(h_sets, num_sets, jitter, d_workspace, workspace_bytes, d_info, (cudaStream_t)stream);
 }
 
 int cbo_build_tables(const cbo_set_desc* h_sets, int num_sets, void* stream) {

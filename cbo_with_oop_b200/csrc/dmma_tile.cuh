@@ -65,4 +65,50 @@ __device__ __forceinline__ void mma_stage(const double* __restrict__ sA, const d
     }
 }
 
+// Mainloop of a warp-tiled 128 x 128 product  acc += sum over nk 16-deep slabs of A[m][k] * B[n][k]  for two
+// "k-contiguous row" operands in global memory (row pitches lda / ldb in doubles, 16-byte aligned rows): a STAGES-deep
+// cp.async ring of fragment-order slabs, one __syncthreads per slab.  Used by the prior-precompute SYRK (K1a) and by the
+// blocked Cholesky / triangular inverse / Ky^-1 kernels of the observational GP fit (K5).  On return every cp.async has
+// landed and every warp has passed a barrier: the caller may reuse the shared memory and may overwrite the operands.
+template <int WM, int WN, int MA, int NB, int STAGES>
+__device__ __forceinline__ void abt_mainloop(const double* __restrict__ gA, size_t lda, const double* __restrict__ gB, size_t ldb,
+                                             int nk, double* sA, double* sB, double (&acc)[MA][NB][2], int tid) {
+    constexpr int BM = WM * MA * 8, BN = WN * NB * 8, NT = WM * WN * 32;
+    constexpr int TA = BM * kBK, TB = BN * kBK;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int row0 = (warp / WN) * MA * 8, col0 = (warp % WN) * NB * 8;
+#pragma unroll 1
+    for (int i = 0; i < STAGES - 1; ++i) {
+        if (i < nk) {
+            load_rows_async<BM, NT>(sA + i * TA, gA + (size_t)i * kBK, lda, tid);
+            load_rows_async<BN, NT>(sB + i * TB, gB + (size_t)i * kBK, ldb, tid);
+        }
+        cp_async_commit();
+    }
+#pragma unroll 1
+    for (int kt = 0; kt < nk; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        const int nx = kt + STAGES - 1;
+        if (nx < nk) {
+            const int ps = nx % STAGES;
+            load_rows_async<BM, NT>(sA + ps * TA, gA + (size_t)nx * kBK, lda, tid);
+            load_rows_async<BN, NT>(sB + ps * TB, gB + (size_t)nx * kBK, ldb, tid);
+        }
+        cp_async_commit();
+        const int cs = kt % STAGES;
+        mma_stage<BM, BN, MA, NB>(sA + cs * TA, sB + cs * TB, acc, row0, col0, lane);
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+}
+
+// lower-triangular tile pair (bi >= bj) from a linear index t = bi (bi + 1) / 2 + bj
+__device__ __forceinline__ void tri_tile(int t, int& bi, int& bj) {
+    bi = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((long long)bi * (bi + 1) / 2 > t) --bi;
+    while ((long long)(bi + 1) * (bi + 2) / 2 <= t) ++bi;
+    bj = t - bi * (bi + 1) / 2;
+}
+
 }  // namespace cbo

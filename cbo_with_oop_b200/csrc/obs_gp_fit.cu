@@ -1,0 +1,339 @@
+// K5 -- exact-inference state of an observational GP on the device:  alpha = Ky^-1 y  and  Ky^-1.
+//
+// Replaces the GPRegression(...) inside fit_gaussian_process (reference utils.py:40-45; GPy ExactGaussianInference:
+// Ky = K + (noise + 1e-8) I, L = jitchol(Ky), alpha = dpotrs(L, y), Ky^-1 = dpotri(L)) for FROZEN hyper-parameters;
+// the hyper-parameter search around it stays on the host (it calls this once per evaluation at large N).
+// Its outputs are the inputs of K1a (alpha_obs, kyinv): SURVEY.md §8(f).2.
+//
+// Everything O(N^3) runs on the FP64 tensor pipe through the 128 x 128 DMMA tile mainloop of dmma_tile.cuh
+// (C += A B^T for two k-contiguous row operands), on an Npad x Npad workspace padded with an identity block:
+//   gram      A = s2 exp(-.5 r^2) + (noise + 1e-8 + jitter) I           r^2 from coordinate differences; N^2 exp
+//   potrf     right-looking blocked Cholesky, 128-column panels: per panel
+//               diag   one CTA: Cholesky of the 128 x 128 diagonal block in shared memory, then its in-place
+//                      triangular inverse Linv_p (also written, transposed, as the diagonal block of Wt)
+//               trsm   A[I,p] <- A[I,p] Linv_p^T   for the row blocks below (a 128-deep tile product)
+//               syrk   A[I,J] -= A[I,p] A[J,p]^T    for p < J <= I        (N^3/3 flops in total)
+//   winv      Wt = L^-T (upper triangular, row-major) by blocked forward substitution over the block rows of W = L^-1:
+//               step1  S[I,J] = sum_{J <= K < I} L[I,K] W[K,J], stored transposed in Wt's (J, I) block
+//               step2  W[I,J] = -Linv_I S[I,J], in place                  (N^3/3 flops)
+//   kyinv     Ky^-1[i][j] = sum_{k >= max(i,j)} Wt[i][k] Wt[j][k], both triangles written (N^3/3 flops)
+//   alpha     z = Wt^T y, alpha = Wt z                                    (two HBM-bound passes over Wt)
+// A non-positive pivot is reported through `info` (1 + the panel index); the caller retries with GPy's jitter rule.
+// Launch-latency bound for small N (3 launches per panel); at N = 1e4 the tile products dominate.
+#include "dmma_tile.cuh"
+
+namespace cbo {
+
+constexpr int kFB = 128;              // block size of the factorisation = tile size of the DMMA mainloop
+constexpr int kFitStages = 4;
+constexpr int kDiagLd = kFB + 1;      // padded pitch of the diagonal block in shared memory (column walks hit all banks)
+
+struct ObsX {
+    const double* col[CBO_MAX_D + CBO_MAX_C];   // one device pointer per GP input column (n_obs doubles each)
+    double il[CBO_MAX_D + CBO_MAX_C];           // 1 / lengthscale
+    int D;
+};
+
+__global__ void __launch_bounds__(256)
+gram_kernel(ObsX X, int n, int npad, double s2, double diag_add, double* __restrict__ A) {
+    const int i = blockIdx.y;
+    double xi[CBO_MAX_D + CBO_MAX_C];
+#pragma unroll
+    for (int k = 0; k < CBO_MAX_D + CBO_MAX_C; ++k) xi[k] = (k < X.D && i < n) ? X.col[k][i] : 0.0;
+    for (int j = blockIdx.x * 256 + threadIdx.x; j < npad; j += gridDim.x * 256) {
+        double v;
+        if (i < n && j < n) {
+            double r2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < CBO_MAX_D + CBO_MAX_C; ++k) {
+                if (k < X.D) {
+                    const double t = (xi[k] - X.col[k][j]) * X.il[k];
+                    r2 = fma(t, t, r2);
+                }
+            }
+            v = s2 * exp(-0.5 * r2) + (i == j ? diag_add : 0.0);
+        } else {
+            v = i == j ? 1.0 : 0.0;     // identity padding: the padded factor, inverse and Ky^-1 stay block diagonal
+        }
+        A[(size_t)i * npad + j] = v;
+    }
+}
+
+// Cholesky + in-place triangular inverse of diagonal block p.  One CTA.
+__global__ void __launch_bounds__(256, 1)
+potrf_diag_kernel(double* __restrict__ A, int ld, int p, double* __restrict__ Linv, double* __restrict__ Wt, int* __restrict__ info) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* B = reinterpret_cast<double*>(smem_raw);          // kFB x kDiagLd
+    double* col = B + kFB * kDiagLd;                            // kFB: the column being eliminated by the inverse
+    __shared__ int fail;
+    const int tid = threadIdx.x;
+    double* __restrict__ blk = A + (size_t)p * kFB * ld + (size_t)p * kFB;
+    for (int e = tid; e < kFB * kFB; e += 256) B[(e / kFB) * kDiagLd + (e % kFB)] = blk[(size_t)(e / kFB) * ld + (e % kFB)];
+    if (tid == 0) fail = 0;
+    __syncthreads();
+    // right-looking Cholesky, lower
+    for (int j = 0; j < kFB; ++j) {
+        if (tid == 0) {
+            const double piv = B[j * kDiagLd + j];
+            if (!(piv > 0.0)) fail = 1;
+            B[j * kDiagLd + j] = sqrt(piv);
+        }
+        __syncthreads();
+        if (fail) break;
+        const double inv = 1.0 / B[j * kDiagLd + j];
+        for (int i = j + 1 + tid; i < kFB; i += 256) B[i * kDiagLd + j] *= inv;
+        __syncthreads();
+        const int rem = kFB - 1 - j;
+        for (int e = tid; e < rem * rem; e += 256) {
+            const int i = j + 1 + e / rem, k = j + 1 + e % rem;
+            if (k <= i) B[i * kDiagLd + k] -= B[i * kDiagLd + j] * B[k * kDiagLd + j];
+        }
+        __syncthreads();
+    }
+    if (fail) {
+        if (tid == 0 && atomicCAS(info, 0, 1 + p) == 0) {}
+        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+        for (int e = tid; e < kFB * kFB; e += 256) {
+            const int i = e / kFB, j = e % kFB;
+            blk[(size_t)i * ld + j] = nan;
+            Linv[e] = nan;
+            Wt[((size_t)p * kFB + i) * ld + (size_t)p * kFB + j] = nan;
+        }
+        return;
+    }
+    for (int e = tid; e < kFB * kFB; e += 256) {   // L_pp (upper part zero) back to the workspace
+        const int i = e / kFB, j = e % kFB;
+        blk[(size_t)i * ld + j] = j <= i ? B[i * kDiagLd + j] : 0.0;
+    }
+    __syncthreads();
+    // in-place inverse of the lower-triangular block, last column first (LAPACK dtrti2, lower):
+    //   W[j][j] = 1 / L[j][j] ;  W[j+1:, j] = -W[j+1:, j+1:] L[j+1:, j] W[j][j]
+    for (int j = kFB - 1; j >= 0; --j) {
+        if (tid == 0) B[j * kDiagLd + j] = 1.0 / B[j * kDiagLd + j];
+        for (int i = j + 1 + tid; i < kFB; i += 256) col[i] = B[i * kDiagLd + j];
+        __syncthreads();
+        const double wjj = B[j * kDiagLd + j];
+        for (int i = j + 1 + tid; i < kFB; i += 256) {
+            double acc = 0.0;
+            for (int k = j + 1; k <= i; ++k) acc = fma(B[i * kDiagLd + k], col[k], acc);
+            B[i * kDiagLd + j] = -acc * wjj;
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < kFB * kFB; e += 256) {
+        const int i = e / kFB, j = e % kFB;
+        const double w = j <= i ? B[i * kDiagLd + j] : 0.0;    // W[i][j]
+        Linv[e] = w;
+        Wt[((size_t)p * kFB + j) * ld + (size_t)p * kFB + i] = w;   // Wt = W^T: diagonal block of L^-T
+    }
+}
+
+// acc fragment -> (row, column) of the 128 x 128 tile: acc[mi][ni][e] is element (row0 + mi*8 + lane/4, col0 + ni*8 + (lane%4)*2 + e)
+template <class F>
+__device__ __forceinline__ void for_each_acc(const double (&acc)[8][4][2], int tid, F&& f) {
+    const int lane = tid & 31, warp = tid >> 5;
+    const int row0 = (warp / 4) * 64, col0 = (warp % 4) * 32;
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi) {
+        const int r = row0 + mi * 8 + (lane >> 2);
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+            const int c = col0 + ni * 8 + (lane & 3) * 2;
+            f(r, c, acc[mi][ni][0], acc[mi][ni][1]);
+        }
+    }
+}
+
+#define CBO_FIT_TILE_PROLOGUE()                                                       \
+    extern __shared__ __align__(16) unsigned char smem_raw[];                         \
+    double* sA = reinterpret_cast<double*>(smem_raw);                                 \
+    double* sB = sA + kFitStages * kFB * kBK;                                         \
+    const int tid = threadIdx.x;                                                      \
+    double acc[8][4][2];                                                              \
+    _Pragma("unroll") for (int mi = 0; mi < 8; ++mi)                                  \
+        _Pragma("unroll") for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+// A[I,p] <- A[I,p] Linv_p^T for I = p + 1 + blockIdx.x
+__global__ void __launch_bounds__(256, 1)
+trsm_panel_kernel(double* __restrict__ A, int ld, int p, const double* __restrict__ Linv) {
+    CBO_FIT_TILE_PROLOGUE();
+    const int I = p + 1 + blockIdx.x;
+    double* __restrict__ blk = A + (size_t)I * kFB * ld + (size_t)p * kFB;
+    abt_mainloop<2, 4, 8, 4, kFitStages>(blk, ld, Linv, kFB, kFB / kBK, sA, sB, acc, tid);
+    for_each_acc(acc, tid, [&](int r, int c, double v0, double v1) {
+        *reinterpret_cast<double2*>(blk + (size_t)r * ld + c) = make_double2(v0, v1);
+    });
+}
+
+// A[I,J] -= A[I,p] A[J,p]^T for the lower block triangle behind panel p
+__global__ void __launch_bounds__(256, 1)
+syrk_update_kernel(double* __restrict__ A, int ld, int p) {
+    CBO_FIT_TILE_PROLOGUE();
+    int bi, bj;
+    tri_tile(blockIdx.x, bi, bj);
+    const int I = p + 1 + bi, J = p + 1 + bj;
+    abt_mainloop<2, 4, 8, 4, kFitStages>(A + (size_t)I * kFB * ld + (size_t)p * kFB, ld, A + (size_t)J * kFB * ld + (size_t)p * kFB, ld,
+                                         kFB / kBK, sA, sB, acc, tid);
+    double* __restrict__ blk = A + (size_t)I * kFB * ld + (size_t)J * kFB;
+    for_each_acc(acc, tid, [&](int r, int c, double v0, double v1) {
+        double2* q = reinterpret_cast<double2*>(blk + (size_t)r * ld + c);
+        double2 o = *q;
+        o.x -= v0, o.y -= v1;
+        *q = o;
+    });
+}
+
+// step 1 of block row I of W = L^-1: S[I,J] = sum_{J <= K < I} L[I,K] W[K,J] for J = blockIdx.x < I; S^T -> Wt's (J, I) block
+__global__ void __launch_bounds__(256, 1)
+winv_step1_kernel(const double* __restrict__ L, double* __restrict__ Wt, int ld, int I) {
+    CBO_FIT_TILE_PROLOGUE();
+    const int J = blockIdx.x;
+    abt_mainloop<2, 4, 8, 4, kFitStages>(L + (size_t)I * kFB * ld + (size_t)J * kFB, ld, Wt + (size_t)J * kFB * ld + (size_t)J * kFB, ld,
+                                         (I - J) * (kFB / kBK), sA, sB, acc, tid);
+    double* __restrict__ blk = Wt + (size_t)J * kFB * ld + (size_t)I * kFB;     // element (n, m) holds S[m][n]
+    for_each_acc(acc, tid, [&](int r, int c, double v0, double v1) {
+        blk[(size_t)c * ld + r] = v0;
+        blk[(size_t)(c + 1) * ld + r] = v1;
+    });
+}
+
+// step 2: W[I,J] = -Linv_I S[I,J]; operand S^T sits in Wt's (J, I) block and is overwritten by W[I,J]^T
+__global__ void __launch_bounds__(256, 1)
+winv_step2_kernel(double* __restrict__ Wt, int ld, int I, const double* __restrict__ Linv) {
+    CBO_FIT_TILE_PROLOGUE();
+    const int J = blockIdx.x;
+    double* __restrict__ blk = Wt + (size_t)J * kFB * ld + (size_t)I * kFB;
+    abt_mainloop<2, 4, 8, 4, kFitStages>(Linv, kFB, blk, ld, kFB / kBK, sA, sB, acc, tid);   // acc[m][n] = sum_k Linv[m][k] S[k][n]
+    for_each_acc(acc, tid, [&](int r, int c, double v0, double v1) {
+        blk[(size_t)c * ld + r] = -v0;
+        blk[(size_t)(c + 1) * ld + r] = -v1;
+    });
+}
+
+// Ky^-1[i][j] = sum_{k >= max(i,j)} Wt[i][k] Wt[j][k]; live N x N corner, row pitch n, both triangles
+__global__ void __launch_bounds__(256, 1)
+kyinv_kernel(const double* __restrict__ Wt, int ld, int n, double* __restrict__ kyinv) {
+    CBO_FIT_TILE_PROLOGUE();
+    int I, J;
+    tri_tile(blockIdx.x, I, J);
+    const int nb = ld / kFB;
+    abt_mainloop<2, 4, 8, 4, kFitStages>(Wt + (size_t)I * kFB * ld + (size_t)I * kFB, ld, Wt + (size_t)J * kFB * ld + (size_t)I * kFB, ld,
+                                         (nb - I) * (kFB / kBK), sA, sB, acc, tid);
+    for_each_acc(acc, tid, [&](int r, int c, double v0, double v1) {
+        const int i = I * kFB + r, j = J * kFB + c;
+        if (i < n) {
+            if (j < n) kyinv[(size_t)i * n + j] = v0;
+            if (j + 1 < n) kyinv[(size_t)i * n + j + 1] = v1;
+            if (I != J) {
+                if (j < n) kyinv[(size_t)j * n + i] = v0;
+                if (j + 1 < n) kyinv[(size_t)(j + 1) * n + i] = v1;
+            }
+        }
+    });
+}
+
+// z[k] = sum_{i <= k} Wt[i][k] y[i]   (one thread per column; a warp reads 256 contiguous bytes of each row)
+__global__ void __launch_bounds__(128)
+wty_kernel(const double* __restrict__ Wt, int ld, int n, const double* __restrict__ y, double* __restrict__ z) {
+    const int k = blockIdx.x * 128 + threadIdx.x;
+    if (k >= ld) return;
+    double acc = 0.0;
+    const int top = k < n ? k : n - 1;
+    for (int i = 0; i <= top; ++i) acc = fma(Wt[(size_t)i * ld + k], y[i], acc);
+    z[k] = k < n ? acc : 0.0;
+}
+
+// alpha[i] = sum_{k >= i} Wt[i][k] z[k]   (one warp per row, fixed lane assignment + butterfly: deterministic)
+__global__ void __launch_bounds__(256)
+wz_kernel(const double* __restrict__ Wt, int ld, int n, const double* __restrict__ z, double* __restrict__ alpha) {
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= n) return;
+    double acc = 0.0;
+    for (int k = (i & ~31) + lane; k < n; k += 32)
+        if (k >= i) acc = fma(Wt[(size_t)i * ld + k], z[k], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) alpha[i] = acc;
+}
+
+static size_t fit_ws_doubles(int npad) {
+    const size_t nb = npad / kFB;
+    return 2 * (size_t)npad * npad + nb * kFB * kFB + (size_t)npad;
+}
+
+size_t obs_gp_workspace_bytes_impl(const cbo_set_desc* h_sets, int num_sets) {
+    size_t m = 0;
+    for (int s = 0; s < num_sets; ++s)
+        if (computes_prior(h_sets[s]) && h_sets[s].y_obs) {
+            const size_t b = fit_ws_doubles(h_sets[s].n_obs_pad) * sizeof(double);
+            if (b > m) m = b;
+        }
+    return m;
+}
+
+int obs_gp_fit_impl(const cbo_set_desc* h_sets, int num_sets, double jitter, void* d_ws, size_t ws_bytes, int32_t* d_info,
+                    cudaStream_t st) {
+    constexpr size_t TILE_SMEM = (size_t)kFitStages * 2 * kFB * kBK * sizeof(double);
+    constexpr size_t DIAG_SMEM = ((size_t)kFB * kDiagLd + kFB) * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        CBO_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
+        CBO_CUDA(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
+        CBO_CUDA(cudaFuncSetAttribute(syrk_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
+        CBO_CUDA(cudaFuncSetAttribute(winv_step1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
+        CBO_CUDA(cudaFuncSetAttribute(winv_step2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
+        CBO_CUDA(cudaFuncSetAttribute(kyinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
+        configured = true;
+    }
+    CBO_REQUIRE(d_info != nullptr, "cbo_obs_gp_fit: d_info is NULL");
+    for (int s = 0; s < num_sets; ++s) {
+        const cbo_set_desc& S = h_sets[s];
+        if (!computes_prior(S) || !S.y_obs) continue;
+        const int n = S.n_obs, npad = S.n_obs_pad, nb = npad / kFB;
+        CBO_REQUIRE(S.alpha_obs && S.kyinv && S.x_obs_int && (S.c == 0 || S.x_obs_cond), "cbo_obs_gp_fit: set %d has a NULL pointer", s);
+        CBO_REQUIRE(d_ws != nullptr && ws_bytes >= fit_ws_doubles(npad) * sizeof(double),
+                    "cbo_obs_gp_fit: workspace of %zu bytes too small for set %d (%zu needed); see cbo_obs_gp_workspace_bytes",
+                    ws_bytes, s, fit_ws_doubles(npad) * sizeof(double));
+        double* A = reinterpret_cast<double*>(d_ws);
+        double* Wt = A + (size_t)npad * npad;
+        double* Linv = Wt + (size_t)npad * npad;
+        double* z = Linv + (size_t)nb * kFB * kFB;
+        int* info = d_info + s;
+        CBO_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
+        ObsX X;
+        X.D = S.d + S.c;
+        for (int k = 0; k < CBO_MAX_D + CBO_MAX_C; ++k) {
+            X.col[k] = k < S.d ? S.x_obs_int + (size_t)k * n : (k < X.D ? S.x_obs_cond + (size_t)(k - S.d) * n : nullptr);
+            X.il[k] = k < S.d ? 1.0 / S.ls_int[k] : (k < X.D ? 1.0 / S.ls_cond[k - S.d] : 0.0);
+        }
+        gram_kernel<<<dim3((npad + 255) / 256 < 8 ? (npad + 255) / 256 : 8, npad), 256, 0, st>>>(X, n, npad, S.s2,
+                                                                                               S.noise + 1e-8 + jitter, A);
+        note_launch();
+        for (int p = 0; p < nb; ++p) {
+            potrf_diag_kernel<<<1, 256, DIAG_SMEM, st>>>(A, npad, p, Linv + (size_t)p * kFB * kFB, Wt, info);
+            note_launch();
+            const int T = nb - p - 1;
+            if (T > 0) {
+                trsm_panel_kernel<<<T, 256, TILE_SMEM, st>>>(A, npad, p, Linv + (size_t)p * kFB * kFB);
+                note_launch();
+                syrk_update_kernel<<<T * (T + 1) / 2, 256, TILE_SMEM, st>>>(A, npad, p);
+                note_launch();
+            }
+        }
+        for (int I = 1; I < nb; ++I) {
+            winv_step1_kernel<<<I, 256, TILE_SMEM, st>>>(A, Wt, npad, I);
+            note_launch();
+            winv_step2_kernel<<<I, 256, TILE_SMEM, st>>>(Wt, npad, I, Linv + (size_t)I * kFB * kFB);
+            note_launch();
+        }
+        kyinv_kernel<<<nb * (nb + 1) / 2, 256, TILE_SMEM, st>>>(Wt, npad, n, const_cast<double*>(S.kyinv));
+        note_launch();
+        wty_kernel<<<(npad + 127) / 128, 128, 0, st>>>(Wt, npad, n, S.y_obs, z);
+        note_launch();
+        wz_kernel<<<(n + 7) / 8, 256, 0, st>>>(Wt, npad, n, z, const_cast<double*>(S.alpha_obs));
+        note_launch();
+        CBO_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+}  // namespace cbo

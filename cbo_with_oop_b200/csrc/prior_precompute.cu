@@ -80,7 +80,7 @@ template <int WM, int WN, int MA, int NB, int STAGES>
 __global__ void __launch_bounds__(WM * WN * 32, 1)
 syrk_kernel(const double* __restrict__ P, int n_mc_pad, const double* __restrict__ kyinv, int n_obs, int n_obs_pad,
             double coef, double* __restrict__ M) {
-    constexpr int BM = WM * MA * 8, BN = WN * NB * 8, NT = WM * WN * 32;
+    constexpr int BM = WM * MA * 8, BN = WN * NB * 8;
     static_assert(BM == BN && BM == CBO_NPAD, "square tiles of CBO_NPAD");
     constexpr int TILE = BM * kBK;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -90,47 +90,16 @@ syrk_kernel(const double* __restrict__ P, int n_mc_pad, const double* __restrict
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp / WN, wn = warp % WN;
     const int row0 = wm * MA * 8, col0 = wn * NB * 8;
-
-    // lower-triangular tile pair (bi >= bj) from the linear block index
-    const int t = blockIdx.x;
-    int bi = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-    while ((long long)bi * (bi + 1) / 2 > t) --bi;
-    while ((long long)(bi + 1) * (bi + 2) / 2 <= t) ++bi;
-    const int bj = t - bi * (bi + 1) / 2;
-
-    const double* __restrict__ gA = P + (size_t)bi * BM * n_mc_pad;
-    const double* __restrict__ gB = P + (size_t)bj * BN * n_mc_pad;
-    const int nk = n_mc_pad / kBK;
+    int bi, bj;
+    tri_tile(blockIdx.x, bi, bj);
 
     double acc[MA][NB][2];
 #pragma unroll
     for (int mi = 0; mi < MA; ++mi)
 #pragma unroll
         for (int ni = 0; ni < NB; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-
-#pragma unroll 1
-    for (int i = 0; i < STAGES - 1; ++i) {
-        if (i < nk) {
-            load_rows_async<BM, NT>(sA + i * TILE, gA + (size_t)i * kBK, n_mc_pad, tid);
-            load_rows_async<BN, NT>(sB + i * TILE, gB + (size_t)i * kBK, n_mc_pad, tid);
-        }
-        cp_async_commit();
-    }
-#pragma unroll 1
-    for (int kt = 0; kt < nk; ++kt) {
-        cp_async_wait<STAGES - 2>();
-        __syncthreads();
-        const int nx = kt + STAGES - 1;
-        if (nx < nk) {
-            const int ps = nx % STAGES;
-            load_rows_async<BM, NT>(sA + ps * TILE, gA + (size_t)nx * kBK, n_mc_pad, tid);
-            load_rows_async<BN, NT>(sB + ps * TILE, gB + (size_t)nx * kBK, n_mc_pad, tid);
-        }
-        cp_async_commit();
-        const int cs = kt % STAGES;
-        mma_stage<BM, BN, MA, NB>(sA + cs * TILE, sB + cs * TILE, acc, row0, col0, lane);
-    }
-    cp_async_wait<0>();
+    abt_mainloop<WM, WN, MA, NB, STAGES>(P + (size_t)bi * BM * n_mc_pad, n_mc_pad, P + (size_t)bj * BN * n_mc_pad, n_mc_pad,
+                                         n_mc_pad / kBK, sA, sB, acc, tid);
 
     // M = coef * Kyinv o Q, zero outside the live N x N corner; mirrored into the upper triangle
 #pragma unroll

@@ -188,26 +188,36 @@ prior_rows_kernel(const cbo_set_desc* __restrict__ sets, RowsShape sh, double* _
     }
 }
 
-// one CTA per (set, pass); thread r adds the partials of its row over (row block, chunk) in index order
-__global__ void __launch_bounds__(kRowsWide)
+// one CTA per (set, pass), one warp per row: lane l adds the partials of items l, l + 32, ... (a fixed assignment), then a
+// fixed butterfly combines the 32 lanes -- the order of the additions never depends on scheduling
+__global__ void __launch_bounds__(32 * kRowsWide)
 prior_rows_finalize_kernel(const cbo_set_desc* __restrict__ sets, RowsShape sh, const double* __restrict__ partials) {
     const int set = blockIdx.x / sh.passes, pass = blockIdx.x % sh.passes;
     const cbo_set_desc& S = sets[set];
-    if (!computes_prior(S) || (int)threadIdx.x >= sh.rmax) return;
-    const int r = rows_first(S) + pass * sh.rmax + threadIdx.x;
-    if (r >= S.n_int) return;
+    const int lane = threadIdx.x, row = threadIdx.y;
+    if (!computes_prior(S)) return;
+    const int r = rows_first(S) + pass * sh.rmax + row;
+    if (r >= S.n_int) return;            // warp-uniform
     double qh = 0.0, ql = 0.0, mh = 0.0, ml = 0.0;
     const int nJ = rows_nJ(S);
-    for (int I = 0; I < nJ; ++I) {
-        const int nslab = (I + 1) * (kMBlkRows / kBK);
-        for (int c = 0; c * kRowsSlabs < nslab; ++c) {
-            const double* p = partials + rows_partial_index(sh, set, pass, I, c) + threadIdx.x * kRowsPartial;
-            dd_add(p[0], p[1], qh, ql);
-            dd_add(p[2], p[3], mh, ml);
-        }
+    for (int e = lane; e < nJ * sh.chunks; e += 32) {
+        const int I = e / sh.chunks, c = e - I * sh.chunks;
+        if (c * kRowsSlabs >= (I + 1) * (kMBlkRows / kBK)) continue;     // the item does not exist (nothing was written)
+        const double* p = partials + rows_partial_index(sh, set, pass, I, c) + row * kRowsPartial;
+        dd_add(p[0], p[1], qh, ql);
+        dd_add(p[2], p[3], mh, ml);
     }
-    S.m_int[r] = mh + ml;
-    S.v_int[r] = ((S.s2 + S.noise) - qh) - ql;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double oh = __shfl_xor_sync(0xffffffffu, qh, o), ol = __shfl_xor_sync(0xffffffffu, ql, o);
+        const double ph = __shfl_xor_sync(0xffffffffu, mh, o), pl = __shfl_xor_sync(0xffffffffu, ml, o);
+        dd_add(oh, ol, qh, ql);
+        dd_add(ph, pl, mh, ml);
+    }
+    if (lane == 0) {
+        S.m_int[r] = mh + ml;
+        S.v_int[r] = ((S.s2 + S.noise) - qh) - ql;
+    }
 }
 
 static RowsShape rows_shape(const cbo_set_desc* h_sets, int num_sets) {
@@ -252,7 +262,7 @@ int prior_rows_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int 
     else prior_rows_kernel<kRowsWide><<<grid, kRowsThreads, 0, st>>>(d_sets, sh, partials);
     note_launch();
     CBO_CUDA(cudaGetLastError());
-    prior_rows_finalize_kernel<<<num_sets * sh.passes, kRowsWide, 0, st>>>(d_sets, sh, partials);
+    prior_rows_finalize_kernel<<<num_sets * sh.passes, dim3(32, sh.rmax), 0, st>>>(d_sets, sh, partials);
     note_launch();
     CBO_CUDA(cudaGetLastError());
     return 0;

@@ -28,8 +28,8 @@ class SetProblem:
     x_obs_int: np.ndarray            # (N, d) intervened columns of the observational GP's training design
     x_obs_cond: np.ndarray           # (N, c) conditioning columns (c may be 0)
     mc_cond: np.ndarray              # (S_mc, c) conditioning samples (reference: the same observational rows)
-    alpha_obs: np.ndarray            # (N,)  Ky^-1 y of the observational GP
-    kyinv: np.ndarray                # (N, N) Ky^-1
+    alpha_obs: Optional[np.ndarray]  # (N,)  Ky^-1 y of the observational GP   } both None + y_obs given: computed on the
+    kyinv: Optional[np.ndarray]      # (N, N) Ky^-1                             } device by cbo_obs_gp_fit (K5)
     ls_int: np.ndarray               # (d,) lengthscales of the intervened columns
     ls_cond: np.ndarray              # (c,)
     s2: float                        # RBF variance
@@ -43,6 +43,7 @@ class SetProblem:
     name: str = ""
     # Caller-supplied causal prior (e.g. produced by DoCalculus closures): m_int, v_int on x_int and, for a grid sweep,
     # m_grid / v_grid over the whole tensor grid.  When set, the observational-GP fields above are ignored.
+    y_obs: Optional[np.ndarray] = None   # (N,) training targets of the observational GP (only needed for the device fit)
     prior_external: bool = False
     m_int: Optional[np.ndarray] = None
     v_int: Optional[np.ndarray] = None
@@ -56,6 +57,11 @@ class SetProblem:
     @property
     def computes_prior(self) -> bool:
         return self.causal and not self.prior_external
+
+    @property
+    def device_fit(self) -> bool:
+        """alpha_obs / kyinv are produced on the device from (x_obs, y_obs) instead of being supplied."""
+        return self.computes_prior and self.kyinv is None
 
     @staticmethod
     def with_external_prior(grid, x_int, y_int, m_int, v_int, m_grid=None, v_grid=None, cost_fix=1.0, cost_variable=False,
@@ -181,6 +187,10 @@ class SweepEngine:
                 b["mc_cond"] = self._dev((max(c * Smc, 1),))
                 b["alpha_obs"] = self._dev((N,))
                 b["kyinv"] = self._dev((N * N,))
+                if pr.device_fit:
+                    if pr.y_obs is None:
+                        raise ValueError(f"set {g}: neither (alpha_obs, kyinv) nor y_obs was given")
+                    b["y_obs"] = self._dev((N,))
                 for k in range(d):
                     b[f"tab{k}"] = self._dev((len(pr.grid[k]) * Np,))
                 b["u_int"] = self._dev((self.ncap * Np,))
@@ -246,7 +256,7 @@ class SweepEngine:
                 for k in range(c):
                     D.ls_cond[k] = float(ls_cond[k])
                 D.x_obs_int, D.x_obs_cond, D.mc_cond = ptr("x_obs_int"), ptr("x_obs_cond"), ptr("mc_cond")
-                D.alpha_obs, D.kyinv = ptr("alpha_obs"), ptr("kyinv")
+                D.alpha_obs, D.kyinv, D.y_obs = ptr("alpha_obs"), ptr("kyinv"), ptr("y_obs")
                 for k in range(d):
                     D.tab[k] = ptr(f"tab{k}")
                 D.u_int, D.pbar, D.w, D.M = ptr("u_int"), ptr("pbar"), ptr("w"), ptr("M")
@@ -311,9 +321,42 @@ class SweepEngine:
                 total += self._h2d(b["x_obs_int"], np.asarray(pr.x_obs_int).T, (li, "x_obs_int"), restage)
                 total += self._h2d(b["x_obs_cond"], np.asarray(pr.x_obs_cond).T, (li, "x_obs_cond"), restage)
                 total += self._h2d(b["mc_cond"], np.asarray(pr.mc_cond).T, (li, "mc_cond"), restage)
-                total += self._h2d(b["alpha_obs"], pr.alpha_obs, (li, "alpha_obs"), restage)
-                total += self._h2d(b["kyinv"], pr.kyinv, (li, "kyinv"), restage)
+                if pr.device_fit:
+                    total += self._h2d(b["y_obs"], pr.y_obs, (li, "y_obs"), restage)
+                    self._obs_fit_stale = True
+                else:
+                    total += self._h2d(b["alpha_obs"], pr.alpha_obs, (li, "alpha_obs"), restage)
+                    total += self._h2d(b["kyinv"], pr.kyinv, (li, "kyinv"), restage)
         return total
+
+    def fit_observational(self):
+        """K5 for every set whose observational-GP state is produced on the device (SetProblem.device_fit): Gram, blocked
+        Cholesky, Ky^-1 and alpha from (x_obs, y_obs), with GPy's jitter-retry rule driven from here
+        (fit_gaussian_process, utils.py:40-45, for frozen hyper-parameters)."""
+        self._obs_fit_stale = False
+        todo = [li for li, g in enumerate(self.active) if self.problems[g].device_fit]
+        if not todo:
+            return
+        self._push_descs()
+        if getattr(self, "fit_ws", None) is None:
+            self.fit_ws = torch.empty((self.lib.cbo_obs_gp_workspace_bytes(self.h_sets, len(self.active)),), dtype=torch.uint8,
+                                      device=self.device)
+            self.fit_info = torch.zeros((max(len(self.active), 1),), dtype=torch.int32, device=self.device)
+        self.obs_fit_tries = {}
+        for li in todo:       # one set at a time: each has its own jitter history
+            pr = self.problems[self.active[li]]
+            h = C.cast(C.byref(self.h_sets, li * C.sizeof(SetDesc)), C.POINTER(SetDesc))
+            jitter, tries = 0.0, 0
+            while True:
+                _lib.check(self.lib.cbo_obs_gp_fit(h, 1, jitter, C.c_void_p(self.fit_ws.data_ptr()), self.fit_ws.numel(),
+                                                   C.c_void_p(self.fit_info.data_ptr()), self._stream()), "cbo_obs_gp_fit")
+                if int(self.fit_info[0].item()) == 0:
+                    break
+                if tries == 5:
+                    raise np.linalg.LinAlgError(f"set {self.active[li]}: observational Gram matrix not positive definite, even with jitter")
+                jitter = (pr.s2 + pr.noise + 1e-8) * 1e-6 if tries == 0 else jitter * 10.0
+                tries += 1
+            self.obs_fit_tries[self.active[li]] = tries
 
     def set_interventional(self, g: int, x_int: np.ndarray, y_int: np.ndarray):
         """Replace the interventional data of global set g (Monitor.add_intervention_data, Monitor.py:148-160)."""
@@ -435,6 +478,8 @@ class SweepEngine:
         """Full post-observation trial: prior precompute + prior on x_int and on the grid + posterior fit +
         EI / cost + argmax (reference CBO.intervene after an observe(), CBO.py:143-173)."""
         ev: list = []
+        if getattr(self, "_obs_fit_stale", False):
+            self._timed("obs_gp_fit", self.fit_observational, ev)
         self._timed("tables", self.build_tables, ev)
         self._timed("prior_precompute", self.prior_precompute, ev)
         self._set_row_begin({})

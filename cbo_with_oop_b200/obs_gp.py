@@ -1,9 +1,9 @@
 """Observational-GP state (alpha = Ky^-1 y, Ky^-1) for frozen hyper-parameters.
 
 These are INPUTS of the sweep: the reference produces them with GPy's exact inference inside
-fit_gaussian_process (utils.py:40-45) whenever the agent observes.  Host SciPy for the shipped graph sizes;
-for N ~ 1e4 the O(N^3) factorisation runs through torch.linalg on the device (plumbing, outside the timed
-sweep; listed as the next row to move into csrc/ in SURVEY.md §8f.2).
+fit_gaussian_process (utils.py:40-45) whenever the agent observes.  `fit_state(..., device=...)` runs the library's own
+blocked Cholesky / triangular inverse on the FP64 tensor pipe (csrc/obs_gp_fit.cu, cbo_obs_gp_fit);
+without a device the small shipped graphs go through host SciPy (host code producing inputs, never on the sweep's path).
 """
 from __future__ import annotations
 
@@ -35,18 +35,57 @@ def fit_state(X: np.ndarray, y: np.ndarray, s2: float, ls, noise: float = 1e-2, 
         kyinv = scipy.linalg.cho_solve((L, True), np.eye(N))
         kyinv = 0.5 * (kyinv + kyinv.T)
         return kyinv @ y, kyinv
-    import torch
-    Z = torch.as_tensor(X / ls.reshape(1, -1), device=device)
-    r2 = torch.cdist(Z, Z, compute_mode="donot_use_mm_for_euclid_dist").square_()
-    Ky = r2.mul_(-0.5).exp_().mul_(s2)
-    Ky.diagonal().add_(noise + GPY_JITTER)
-    L = torch.linalg.cholesky(Ky)
-    del Ky
-    kyinv = torch.cholesky_inverse(L)
-    del L
-    kyinv = 0.5 * (kyinv + kyinv.T)
-    alpha = kyinv @ torch.as_tensor(y, device=device)
+    alpha, kyinv, _ = fit_state_device(X, y, s2, ls, noise, device)
     return alpha.cpu().numpy(), kyinv.cpu().numpy()
+
+
+def fit_state_device(X, y, s2: float, ls, noise: float = 1e-2, device="cuda:0", max_tries: int = 5):
+    """(alpha (N,), kyinv (N, N), jitter retries) as float64 torch tensors on `device`, computed by cbo_obs_gp_fit.
+    GPy's jitchol rule on a non-positive pivot: retry with mean(diag Ky) * 1e-6 * 10^t added to the diagonal, t = 0..4."""
+    import ctypes as C
+
+    import torch
+
+    from . import _lib
+    lib = _lib.load()
+    dev = torch.device(device)
+    X = np.ascontiguousarray(np.asarray(X, np.float64))
+    N, D = X.shape
+    if D > _lib.CBO_MAX_D + _lib.CBO_MAX_C:
+        raise ValueError(f"the observational GP has {D} input columns; the library takes {_lib.CBO_MAX_D + _lib.CBO_MAX_C}")
+    ls = np.broadcast_to(np.asarray(ls, np.float64).reshape(-1), (D,))
+    d = min(D, _lib.CBO_MAX_D)
+    h = (_lib.SetDesc * 1)()
+    S = h[0]
+    S.d, S.c, S.n_obs, S.n_obs_pad, S.n_int, S.causal = d, D - d, N, -(-N // _lib.CBO_NPAD) * _lib.CBO_NPAD, 1, 1
+    S.n_mc, S.n_mc_pad = 1, _lib.CBO_SPAD
+    S.p[0], S.g_total, S.g_begin, S.g_count = 1, 1, 0, 0
+    for k in range(1, _lib.CBO_MAX_D):
+        S.p[k] = 1
+    for k in range(d):
+        S.ls_int[k] = float(ls[k])
+    for k in range(D - d):
+        S.ls_cond[k] = float(ls[d + k])
+    S.s2, S.noise, S.cost_fix = float(s2), float(noise), 1.0
+    xt = torch.from_numpy(np.ascontiguousarray(X.T)).to(dev)          # (D, N): one contiguous row per input column
+    yt = torch.from_numpy(np.ascontiguousarray(np.asarray(y, np.float64).reshape(-1))).to(dev)
+    alpha = torch.empty((N,), dtype=torch.float64, device=dev)
+    kyinv = torch.empty((N, N), dtype=torch.float64, device=dev)
+    info = torch.zeros((1,), dtype=torch.int32, device=dev)
+    S.x_obs_int, S.x_obs_cond = xt.data_ptr(), xt.data_ptr() + d * N * 8
+    S.y_obs, S.alpha_obs, S.kyinv = yt.data_ptr(), alpha.data_ptr(), kyinv.data_ptr()
+    ws = torch.empty((lib.cbo_obs_gp_workspace_bytes(h, 1),), dtype=torch.uint8, device=dev)
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    jitter, tries = 0.0, 0
+    while True:
+        _lib.check(lib.cbo_obs_gp_fit(h, 1, jitter, C.c_void_p(ws.data_ptr()), ws.numel(), C.c_void_p(info.data_ptr()), stream),
+                   "cbo_obs_gp_fit")
+        if int(info.item()) == 0:
+            return alpha, kyinv, tries
+        if tries == max_tries:
+            raise np.linalg.LinAlgError("observational Gram matrix not positive definite, even with jitter")
+        jitter = (s2 + noise + GPY_JITTER) * 1e-6 if tries == 0 else jitter * 10.0
+        tries += 1
 
 
 def neg_log_marginal_likelihood(theta, X, y, ard, noise):

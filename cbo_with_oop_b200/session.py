@@ -29,6 +29,8 @@ class AcquisitionSession:
     # ---- stage guards ------------------------------------------------------------------------------
     def _ensure_prior(self):
         if not self.prior_ready:
+            if getattr(self.engine, "_obs_fit_stale", False):
+                self.engine.fit_observational()
             self.engine.build_tables()
             self.engine.prior_precompute()
             self.prior_ready = True

@@ -30,7 +30,7 @@ extern "C" {
 #define CBO_API
 #endif
 
-#define CBO_ABI_VERSION 4
+#define CBO_ABI_VERSION 5
 #define CBO_MAX_D 4          /* intervened dimensions per exploration set (reference uses 1..3) */
 #define CBO_MAX_C 8          /* conditioning dimensions of an observational GP */
 #define CBO_MAX_NINT 128     /* interventional rows per set (reference: 10 .. ~50) */
@@ -103,6 +103,8 @@ typedef struct cbo_set_desc {
     int32_t int_row_begin;     /* cbo_prior_eval which=1 evaluates the interventional rows [int_row_begin, n_int) and leaves
                                   m_int / v_int of the earlier rows untouched (a post-intervention trial appends one row);
                                   0 = all rows */
+    const double* y_obs;       /* (n_obs) training targets of the observational GP; only read by cbo_obs_gp_fit, which WRITES
+                                  alpha_obs and kyinv from them (NULL: the caller supplies alpha_obs / kyinv itself) */
     const double* points;      /* NULL: tensor grid.  Otherwise (g_total, d) row-major candidates; then p[0] = g_total,
                                   p[1..] = 1, grid[] is unused and tab[0] is the (g_total, n_obs_pad) exp table of the points */
 } cbo_set_desc;
@@ -133,6 +135,17 @@ CBO_API unsigned long long cbo_launch_count(void);
 /* Number of sweep work items (tiles of CBO_SWEEP_TILE candidates) for this descriptor list; host-side
  * arithmetic only.  Callers size `d_tile_best` with it. */
 CBO_API long cbo_sweep_num_items(const cbo_set_desc* h_sets, int num_sets);
+
+/* K5. exact-inference state of the observational GPs on the device: for every set with y_obs != NULL,
+ *   Ky = s2 exp(-.5 r^2) + (noise + 1e-8 + jitter) I ,  L = chol(Ky) ,  alpha_obs = Ky^-1 y_obs ,  kyinv = Ky^-1
+ * written through the descriptor's alpha_obs / kyinv pointers (blocked Cholesky, triangular inverse and L^-T L^-1 on the
+ * FP64 tensor pipe).  Replaces the GPRegression(...) inside fit_gaussian_process (utils.py:40-45; GPy exact inference with
+ * dpotrs / dpotri) for frozen hyper-parameters.  d_info[s] = 0 ok, 1 + panel index when a pivot was not positive: the
+ * caller retries with jitter = mean(diag Ky) * 1e-6 * 10^t (GPy's jitchol rule).  Sets are processed one after the other
+ * in the same workspace (cbo_obs_gp_workspace_bytes: the largest set's 2 Npad^2 + O(Npad) doubles). */
+CBO_API size_t cbo_obs_gp_workspace_bytes(const cbo_set_desc* h_sets, int num_sets);
+CBO_API int cbo_obs_gp_fit(const cbo_set_desc* h_sets, int num_sets, double jitter, void* d_workspace, size_t workspace_bytes,
+                           int32_t* d_info, void* stream);
 
 /* K0. exp tables: tab[k][i][j] = exp(-.5 ((grid[k][i] - x_obs_int[k][j]) / ls_int[k])^2) and
  * u_int[i][j] = exp(-.5 sum_k ((x_int[i][k] - x_obs_int[k][j]) / ls_int[k])^2).
