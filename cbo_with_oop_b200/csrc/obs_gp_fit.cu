@@ -13,11 +13,14 @@
 //                      triangular inverse Linv_p (also written, transposed, as the diagonal block of Wt)
 //               trsm   A[I,p] <- A[I,p] Linv_p^T   for the row blocks below (a 128-deep tile product)
 //               syrk   A[I,J] -= A[I,p] A[J,p]^T    for p < J <= I        (N^3/3 flops in total)
-//   winv      Wt = L^-T (upper triangular, row-major) by blocked forward substitution over the block rows of W = L^-1:
-//               step1  S[I,J] = sum_{J <= K < I} L[I,K] W[K,J], stored transposed in Wt's (J, I) block
-//               step2  W[I,J] = -Linv_I S[I,J], in place                  (N^3/3 flops)
+//   winv      Wt = L^-T (upper triangular, row-major): right-looking blocked solve of L W = I, carried out on the
+//             transposes so that every operand is k-contiguous and every store lands in natural layout.  Wt starts as
+//             zero with the diagonal blocks Linv_K^T; for K = 0 .. nb-1
+//               scale   Wt[J,K] <- Wt[J,K] Linv_K^T            for J < K   (block row K of W is final)
+//               update  Wt[J,I] -= Wt[J,K] L[I,K]^T            for J <= K < I   (128-deep tile products, (nb-K-1)(K+1)
+//                                                                               independent tiles per step; N^3/3 flops)
 //   kyinv     Ky^-1[i][j] = sum_{k >= max(i,j)} Wt[i][k] Wt[j][k], both triangles written (N^3/3 flops)
-//   alpha     z = Wt^T y, alpha = Wt z                                    (two HBM-bound passes over Wt)
+//   alpha     z = Wt^T y (partial sums over row chunks, added in order), alpha = Wt z     (two HBM-bound passes over Wt)
 // A non-positive pivot is reported through `info` (1 + the panel index); the caller retries with GPy's jitter rule.
 // Launch-latency bound for small N (3 launches per panel); at N = 1e4 the tile products dominate.
 #include "dmma_tile.cuh"
@@ -83,10 +86,9 @@ potrf_diag_kernel(double* __restrict__ A, int ld, int p, double* __restrict__ Li
         const double inv = 1.0 / B[j * kDiagLd + j];
         for (int i = j + 1 + tid; i < kFB; i += 256) B[i * kDiagLd + j] *= inv;
         __syncthreads();
-        const int rem = kFB - 1 - j;
-        for (int e = tid; e < rem * rem; e += 256) {
-            const int i = j + 1 + e / rem, k = j + 1 + e % rem;
-            if (k <= i) B[i * kDiagLd + k] -= B[i * kDiagLd + j] * B[k * kDiagLd + j];
+        for (int i = j + 1 + (tid >> 4); i < kFB; i += 16) {      // 16 x 16 threads over (row i, column k <= i)
+            const double lij = B[i * kDiagLd + j];
+            for (int k = j + 1 + (tid & 15); k <= i; k += 16) B[i * kDiagLd + k] = fma(-lij, B[k * kDiagLd + j], B[i * kDiagLd + k]);
         }
         __syncthreads();
     }
@@ -183,30 +185,31 @@ syrk_update_kernel(double* __restrict__ A, int ld, int p) {
     });
 }
 
-// step 1 of block row I of W = L^-1: S[I,J] = sum_{J <= K < I} L[I,K] W[K,J] for J = blockIdx.x < I; S^T -> Wt's (J, I) block
+// Wt[J,K] <- Wt[J,K] Linv_K^T for J = blockIdx.x < K: block row K of W = L^-1 becomes final (held transposed)
 __global__ void __launch_bounds__(256, 1)
-winv_step1_kernel(const double* __restrict__ L, double* __restrict__ Wt, int ld, int I) {
+winv_scale_kernel(double* __restrict__ Wt, int ld, int K, const double* __restrict__ Linv) {
     CBO_FIT_TILE_PROLOGUE();
     const int J = blockIdx.x;
-    abt_mainloop<2, 4, 8, 4, kFitStages>(L + (size_t)I * kFB * ld + (size_t)J * kFB, ld, Wt + (size_t)J * kFB * ld + (size_t)J * kFB, ld,
-                                         (I - J) * (kFB / kBK), sA, sB, acc, tid);
-    double* __restrict__ blk = Wt + (size_t)J * kFB * ld + (size_t)I * kFB;     // element (n, m) holds S[m][n]
+    double* __restrict__ blk = Wt + (size_t)J * kFB * ld + (size_t)K * kFB;
+    abt_mainloop<2, 4, 8, 4, kFitStages>(blk, ld, Linv, kFB, kFB / kBK, sA, sB, acc, tid);   // acc[n][m] = sum_k R^T[n][k] Linv[m][k]
     for_each_acc(acc, tid, [&](int r, int c, double v0, double v1) {
-        blk[(size_t)c * ld + r] = v0;
-        blk[(size_t)(c + 1) * ld + r] = v1;
+        *reinterpret_cast<double2*>(blk + (size_t)r * ld + c) = make_double2(v0, v1);
     });
 }
 
-// step 2: W[I,J] = -Linv_I S[I,J]; operand S^T sits in Wt's (J, I) block and is overwritten by W[I,J]^T
+// Wt[J,I] -= Wt[J,K] L[I,K]^T for I = K + 1 + blockIdx.x, J = blockIdx.y <= K: the running right-hand side of the rows below K
 __global__ void __launch_bounds__(256, 1)
-winv_step2_kernel(double* __restrict__ Wt, int ld, int I, const double* __restrict__ Linv) {
+winv_update_kernel(const double* __restrict__ L, double* __restrict__ Wt, int ld, int K) {
     CBO_FIT_TILE_PROLOGUE();
-    const int J = blockIdx.x;
+    const int I = K + 1 + blockIdx.x, J = blockIdx.y;
+    abt_mainloop<2, 4, 8, 4, kFitStages>(Wt + (size_t)J * kFB * ld + (size_t)K * kFB, ld, L + (size_t)I * kFB * ld + (size_t)K * kFB, ld,
+                                         kFB / kBK, sA, sB, acc, tid);
     double* __restrict__ blk = Wt + (size_t)J * kFB * ld + (size_t)I * kFB;
-    abt_mainloop<2, 4, 8, 4, kFitStages>(Linv, kFB, blk, ld, kFB / kBK, sA, sB, acc, tid);   // acc[m][n] = sum_k Linv[m][k] S[k][n]
     for_each_acc(acc, tid, [&](int r, int c, double v0, double v1) {
-        blk[(size_t)c * ld + r] = -v0;
-        blk[(size_t)(c + 1) * ld + r] = -v1;
+        double2* q = reinterpret_cast<double2*>(blk + (size_t)r * ld + c);
+        double2 o = *q;
+        o.x -= v0, o.y -= v1;
+        *q = o;
     });
 }
 
@@ -232,15 +235,25 @@ kyinv_kernel(const double* __restrict__ Wt, int ld, int n, double* __restrict__ 
     });
 }
 
-// z[k] = sum_{i <= k} Wt[i][k] y[i]   (one thread per column; a warp reads 256 contiguous bytes of each row)
+// z[k] = sum_{i <= k} Wt[i][k] y[i]: grid (column tile, row chunk); a thread owns one column of one chunk of 256 rows and
+// writes one partial; wty_reduce_kernel adds the chunks in order (deterministic)
+constexpr int kWtyRows = 256;
 __global__ void __launch_bounds__(128)
-wty_kernel(const double* __restrict__ Wt, int ld, int n, const double* __restrict__ y, double* __restrict__ z) {
-    const int k = blockIdx.x * 128 + threadIdx.x;
-    if (k >= ld) return;
+wty_kernel(const double* __restrict__ Wt, int ld, int n, const double* __restrict__ y, double* __restrict__ part) {
+    const int k = blockIdx.x * 128 + threadIdx.x, i0 = blockIdx.y * kWtyRows;
     double acc = 0.0;
-    const int top = k < n ? k : n - 1;
-    for (int i = 0; i <= top; ++i) acc = fma(Wt[(size_t)i * ld + k], y[i], acc);
-    z[k] = k < n ? acc : 0.0;
+    if (k < n) {
+        const int top = k < i0 + kWtyRows - 1 ? k : i0 + kWtyRows - 1;   // rows i0 .. top (i <= k: Wt is upper triangular)
+        for (int i = i0; i <= top; ++i) acc = fma(Wt[(size_t)i * ld + k], y[i], acc);
+    }
+    part[(size_t)blockIdx.y * ld + k] = acc;
+}
+__global__ void __launch_bounds__(128)
+wty_reduce_kernel(const double* __restrict__ part, int ld, int chunks, double* __restrict__ z) {
+    const int k = blockIdx.x * 128 + threadIdx.x;
+    double acc = 0.0;
+    for (int c = 0; c < chunks; ++c) acc += part[(size_t)c * ld + k];
+    z[k] = acc;
 }
 
 // alpha[i] = sum_{k >= i} Wt[i][k] z[k]   (one warp per row, fixed lane assignment + butterfly: deterministic)
@@ -256,8 +269,8 @@ wz_kernel(const double* __restrict__ Wt, int ld, int n, const double* __restrict
 }
 
 static size_t fit_ws_doubles(int npad) {
-    const size_t nb = npad / kFB;
-    return 2 * (size_t)npad * npad + nb * kFB * kFB + (size_t)npad;
+    const size_t nb = npad / kFB, chunks = (npad + kWtyRows - 1) / kWtyRows;
+    return 2 * (size_t)npad * npad + nb * kFB * kFB + (size_t)npad * (1 + chunks);   // A, Wt, Linv blocks, z, z partials
 }
 
 size_t obs_gp_workspace_bytes_impl(const cbo_set_desc* h_sets, int num_sets) {
@@ -279,8 +292,8 @@ int obs_gp_fit_impl(const cbo_set_desc* h_sets, int num_sets, double jitter, voi
         CBO_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
         CBO_CUDA(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
         CBO_CUDA(cudaFuncSetAttribute(syrk_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
-        CBO_CUDA(cudaFuncSetAttribute(winv_step1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
-        CBO_CUDA(cudaFuncSetAttribute(winv_step2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
+        CBO_CUDA(cudaFuncSetAttribute(winv_scale_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
+        CBO_CUDA(cudaFuncSetAttribute(winv_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
         CBO_CUDA(cudaFuncSetAttribute(kyinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
         configured = true;
     }
@@ -297,6 +310,8 @@ int obs_gp_fit_impl(const cbo_set_desc* h_sets, int num_sets, double jitter, voi
         double* Wt = A + (size_t)npad * npad;
         double* Linv = Wt + (size_t)npad * npad;
         double* z = Linv + (size_t)nb * kFB * kFB;
+        double* zpart = z + npad;
+        const int chunks = (npad + kWtyRows - 1) / kWtyRows;
         int* info = d_info + s;
         CBO_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
         ObsX X;
@@ -305,6 +320,7 @@ int obs_gp_fit_impl(const cbo_set_desc* h_sets, int num_sets, double jitter, voi
             X.col[k] = k < S.d ? S.x_obs_int + (size_t)k * n : (k < X.D ? S.x_obs_cond + (size_t)(k - S.d) * n : nullptr);
             X.il[k] = k < S.d ? 1.0 / S.ls_int[k] : (k < X.D ? 1.0 / S.ls_cond[k - S.d] : 0.0);
         }
+        CBO_CUDA(cudaMemsetAsync(Wt, 0, (size_t)npad * npad * sizeof(double), st));   // right-hand side of L W = I, off-diagonal part
         gram_kernel<<<dim3((npad + 255) / 256 < 8 ? (npad + 255) / 256 : 8, npad), 256, 0, st>>>(X, n, npad, S.s2,
                                                                                                S.noise + 1e-8 + jitter, A);
         note_launch();
@@ -319,15 +335,23 @@ int obs_gp_fit_impl(const cbo_set_desc* h_sets, int num_sets, double jitter, voi
                 note_launch();
             }
         }
-        for (int I = 1; I < nb; ++I) {
-            winv_step1_kernel<<<I, 256, TILE_SMEM, st>>>(A, Wt, npad, I);
+        for (int K = 0; K + 1 < nb; ++K) {
+            if (K > 0) {
+                winv_scale_kernel<<<K, 256, TILE_SMEM, st>>>(Wt, npad, K, Linv + (size_t)K * kFB * kFB);
+                note_launch();
+            }
+            winv_update_kernel<<<dim3(nb - K - 1, K + 1), 256, TILE_SMEM, st>>>(A, Wt, npad, K);
             note_launch();
-            winv_step2_kernel<<<I, 256, TILE_SMEM, st>>>(Wt, npad, I, Linv + (size_t)I * kFB * kFB);
+        }
+        if (nb > 1) {
+            winv_scale_kernel<<<nb - 1, 256, TILE_SMEM, st>>>(Wt, npad, nb - 1, Linv + (size_t)(nb - 1) * kFB * kFB);
             note_launch();
         }
         kyinv_kernel<<<nb * (nb + 1) / 2, 256, TILE_SMEM, st>>>(Wt, npad, n, const_cast<double*>(S.kyinv));
         note_launch();
-        wty_kernel<<<(npad + 127) / 128, 128, 0, st>>>(Wt, npad, n, S.y_obs, z);
+        wty_kernel<<<dim3(npad / 128, chunks), 128, 0, st>>>(Wt, npad, n, S.y_obs, zpart);
+        note_launch();
+        wty_reduce_kernel<<<npad / 128, 128, 0, st>>>(zpart, npad, chunks, z);
         note_launch();
         wz_kernel<<<(n + 7) / 8, 256, 0, st>>>(Wt, npad, n, z, const_cast<double*>(S.alpha_obs));
         note_launch();
