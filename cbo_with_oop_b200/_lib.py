@@ -52,7 +52,7 @@ class SweepResult(C.Structure):
 EXPORTS = [
     "cbo_abi_version", "cbo_sizeof_set_desc", "cbo_offsetof_set_desc", "cbo_last_error", "cbo_sweep_num_items",
     "cbo_prior_workspace_bytes", "cbo_launch_count", "cbo_obs_gp_workspace_bytes",
-    "cbo_obs_gp_fit",
+    "cbo_obs_gp_fit", "cbo_obs_gp_nll",
     "cbo_build_tables", "cbo_prior_precompute", "cbo_prior_eval", "cbo_posterior_fit", "cbo_sweep",
     "cbo_argmax_combine",
 ]
@@ -93,6 +93,7 @@ def load() -> C.CDLL:
     lib.cbo_obs_gp_workspace_bytes.restype = C.c_size_t
     lib.cbo_obs_gp_workspace_bytes.argtypes = [P, C.c_int]
     lib.cbo_obs_gp_fit.argtypes = [P, C.c_int, C.c_double, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    lib.cbo_obs_gp_nll.argtypes = [P, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     lib.cbo_prior_eval.argtypes = [P, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.cbo_posterior_fit.argtypes = [P, C.c_void_p, C.c_int, C.c_void_p]
     lib.cbo_sweep.argtypes = [P, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,

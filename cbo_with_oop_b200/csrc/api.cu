@@ -67,6 +67,7 @@ int sweep_impl(const cbo_set_desc*, const cbo_set_desc*, int, double, int, cbo_s
 int argmax_combine_impl(const cbo_set_best*, int, int, cbo_set_best*, cbo_sweep_result*, cudaStream_t);
 size_t obs_gp_workspace_bytes_impl(const cbo_set_desc*, int);
 int obs_gp_fit_impl(const cbo_set_desc*, int, double, void*, size_t, int32_t*, cudaStream_t);
+int obs_gp_nll_impl(const cbo_set_desc*, void*, size_t, double*, cudaStream_t);
 
 }  // namespace cbo
 
@@ -107,6 +108,11 @@ int cbo_obs_gp_fit(const cbo_set_desc* h_sets, int num_sets, double jitter, void
     if (int rc = validate_sets(h_sets, num_sets)) return rc;
     CBO_REQUIRE(jitter >= 0.0, "cbo_obs_gp_fit: jitter must be non-negative");
     return obs_gp_fit_impl(h_sets, num_sets, jitter, d_workspace, workspace_bytes, d_info, (cudaStream_t)stream);
+}
+
+int cbo_obs_gp_nll(const cbo_set_desc* h_set, void* d_workspace, size_t workspace_bytes, double* d_out, void* stream) {
+    if (int rc = validate_sets(h_set, 1)) return rc;
+    return obs_gp_nll_impl(h_set, d_workspace, workspace_bytes, d_out, (cudaStream_t)stream);
 }
 
 int cbo_build_tables(const cbo_set_desc* h_sets, int num_sets, void* stream) {

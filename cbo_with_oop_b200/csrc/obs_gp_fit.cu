@@ -268,9 +268,81 @@ wz_kernel(const double* __restrict__ Wt, int ld, int n, const double* __restrict
     if (lane == 0) alpha[i] = acc;
 }
 
+// ---- negative log marginal likelihood and its gradient (the objective of gp.optimize(), utils.py:44) ---------------------
+//   nll = 0.5 y.alpha + sum_i log L_ii + 0.5 N log(2 pi)
+//   d nll / d log s2  = -0.5 sum_ij W_ij K_ij ,  d nll / d log l_k = -0.5 sum_ij W_ij K_ij ((x_ik - x_jk) / l_k)^2 ,
+//   W = alpha alpha^T - Ky^-1 ,  K = s2 exp(-.5 r^2)  (the noise is fixed, utils.py:43)
+// One CTA per row i recomputes K_ij on the fly and reduces its 1 + D sums in a fixed order; a second kernel adds the rows.
+constexpr int kNllTerms = 1 + CBO_MAX_D + CBO_MAX_C;
+
+__global__ void __launch_bounds__(256)
+nll_rows_kernel(ObsX X, int n, double s2, const double* __restrict__ alpha, const double* __restrict__ kyinv, double* __restrict__ part) {
+    __shared__ double red[8][kNllTerms];
+    const int i = blockIdx.x, tid = threadIdx.x;
+    double xi[CBO_MAX_D + CBO_MAX_C], acc[kNllTerms];
+#pragma unroll
+    for (int k = 0; k < CBO_MAX_D + CBO_MAX_C; ++k) xi[k] = k < X.D ? X.col[k][i] : 0.0;
+#pragma unroll
+    for (int t = 0; t < kNllTerms; ++t) acc[t] = 0.0;
+    const double ai = alpha[i];
+    for (int j = tid; j < n; j += 256) {
+        double dk[CBO_MAX_D + CBO_MAX_C], r2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < CBO_MAX_D + CBO_MAX_C; ++k) {
+            dk[k] = 0.0;
+            if (k < X.D) {
+                const double t = (xi[k] - X.col[k][j]) * X.il[k];
+                dk[k] = t * t;
+                r2 += dk[k];
+            }
+        }
+        const double wk = (ai * alpha[j] - kyinv[(size_t)i * n + j]) * (s2 * exp(-0.5 * r2));
+        acc[0] += wk;
+#pragma unroll
+        for (int k = 0; k < CBO_MAX_D + CBO_MAX_C; ++k) acc[1 + k] = fma(wk, dk[k], acc[1 + k]);
+    }
+#pragma unroll
+    for (int t = 0; t < kNllTerms; ++t) {
+        const double v = warp_sum(acc[t]);
+        if ((tid & 31) == 0) red[tid >> 5][t] = v;
+    }
+    __syncthreads();
+    if (tid < kNllTerms) {
+        double v = 0.0;
+#pragma unroll
+        for (int wq = 0; wq < 8; ++wq) v += red[wq][tid];
+        part[(size_t)i * kNllTerms + tid] = v;
+    }
+}
+
+// out[0] = nll, out[1] = d/dlog s2, out[2 + k] = d/dlog l_k; one CTA, fixed summation order
+__global__ void __launch_bounds__(256)
+nll_reduce_kernel(const double* __restrict__ part, int n, int D, const double* __restrict__ L, int ld, const double* __restrict__ y,
+                  const double* __restrict__ alpha, double* __restrict__ out) {
+    __shared__ double red[8];
+    const int tid = threadIdx.x;
+    for (int t = 0; t < 2 + kNllTerms; ++t) {          // t = 0: y.alpha, 1: sum log L_ii, 2..: the gradient sums
+        double v = 0.0;
+        for (int i = tid; i < n; i += 256)
+            v += t == 0 ? y[i] * alpha[i] : (t == 1 ? log(L[(size_t)i * ld + i]) : part[(size_t)i * kNllTerms + (t - 2)]);
+        v = warp_sum(v);
+        if ((tid & 31) == 0) red[tid >> 5] = v;
+        __syncthreads();
+        if (tid == 0) {
+            double tot = 0.0;
+            for (int wq = 0; wq < 8; ++wq) tot += red[wq];
+            if (t == 0) out[0] = 0.5 * tot + 0.5 * (double)n * 1.8378770664093454836;   // log(2 pi)
+            else if (t == 1) out[0] += tot;
+            else if (t - 2 < 1 + D) out[t - 1] = -0.5 * tot;
+        }
+        __syncthreads();
+    }
+}
+
 static size_t fit_ws_doubles(int npad) {
     const size_t nb = npad / kFB, chunks = (npad + kWtyRows - 1) / kWtyRows;
-    return 2 * (size_t)npad * npad + nb * kFB * kFB + (size_t)npad * (1 + chunks);   // A, Wt, Linv blocks, z, z partials
+    const size_t zpart = (size_t)npad * chunks, nllpart = (size_t)npad * kNllTerms;        // the two never live together
+    return 2 * (size_t)npad * npad + nb * kFB * kFB + (size_t)npad + (zpart > nllpart ? zpart : nllpart);   // A, Wt, Linv, z, partials
 }
 
 size_t obs_gp_workspace_bytes_impl(const cbo_set_desc* h_sets, int num_sets) {
@@ -357,6 +429,30 @@ int obs_gp_fit_impl(const cbo_set_desc* h_sets, int num_sets, double jitter, voi
         note_launch();
         CBO_CUDA(cudaGetLastError());
     }
+    return 0;
+}
+
+// nll and gradient of ONE set from the state cbo_obs_gp_fit left behind: L in the workspace, alpha_obs / kyinv in the descriptor
+int obs_gp_nll_impl(const cbo_set_desc* h_set, void* d_ws, size_t ws_bytes, double* d_out, cudaStream_t st) {
+    const cbo_set_desc& S = *h_set;
+    CBO_REQUIRE(computes_prior(S) && S.y_obs && S.alpha_obs && S.kyinv, "cbo_obs_gp_nll: the set has no device-fitted observational GP");
+    const int n = S.n_obs, npad = S.n_obs_pad, nb = npad / kFB;
+    CBO_REQUIRE(d_ws != nullptr && ws_bytes >= fit_ws_doubles(npad) * sizeof(double) && d_out != nullptr,
+                "cbo_obs_gp_nll: needs the workspace of the preceding cbo_obs_gp_fit (%zu bytes) and an output buffer",
+                fit_ws_doubles(npad) * sizeof(double));
+    double* A = reinterpret_cast<double*>(d_ws);
+    double* part = A + 2 * (size_t)npad * npad + (size_t)nb * kFB * kFB + npad;
+    ObsX X;
+    X.D = S.d + S.c;
+    for (int k = 0; k < CBO_MAX_D + CBO_MAX_C; ++k) {
+        X.col[k] = k < S.d ? S.x_obs_int + (size_t)k * n : (k < X.D ? S.x_obs_cond + (size_t)(k - S.d) * n : nullptr);
+        X.il[k] = k < S.d ? 1.0 / S.ls_int[k] : (k < X.D ? 1.0 / S.ls_cond[k - S.d] : 0.0);
+    }
+    nll_rows_kernel<<<n, 256, 0, st>>>(X, n, S.s2, S.alpha_obs, S.kyinv, part);
+    note_launch();
+    nll_reduce_kernel<<<1, 256, 0, st>>>(part, n, X.D, A, npad, S.y_obs, S.alpha_obs, d_out);
+    note_launch();
+    CBO_CUDA(cudaGetLastError());
     return 0;
 }
 

@@ -147,6 +147,13 @@ CBO_API size_t cbo_obs_gp_workspace_bytes(const cbo_set_desc* h_sets, int num_se
 CBO_API int cbo_obs_gp_fit(const cbo_set_desc* h_sets, int num_sets, double jitter, void* d_workspace, size_t workspace_bytes,
                            int32_t* d_info, void* stream);
 
+/* Objective of the hyper-parameter search around K5 (gp.optimize() in fit_gaussian_process, utils.py:44), for ONE set whose
+ * state was just produced by cbo_obs_gp_fit in the same workspace:
+ *   d_out[0] = -log p(y | X, s2, l) = 0.5 y.alpha + sum log L_ii + 0.5 N log(2 pi)
+ *   d_out[1] = d/d log s2 ,  d_out[2 + k] = d/d log l_k  (k over the intervened, then the conditioning columns; sum them
+ *   for a shared lengthscale); the noise is fixed (utils.py:43).  d_out: 2 + d + c device doubles. */
+CBO_API int cbo_obs_gp_nll(const cbo_set_desc* h_set, void* d_workspace, size_t workspace_bytes, double* d_out, void* stream);
+
 /* K0. exp tables: tab[k][i][j] = exp(-.5 ((grid[k][i] - x_obs_int[k][j]) / ls_int[k])^2) and
  * u_int[i][j] = exp(-.5 sum_k ((x_int[i][k] - x_obs_int[k][j]) / ls_int[k])^2).
  * Replaces the kernel evaluations inside gp.predict at DoCalculus.py:77 for the intervened columns. */

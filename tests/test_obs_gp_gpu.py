@@ -99,3 +99,32 @@ def test_large_fit_properties(cuda_engine_ready):
     assert torch.equal(kyinv, kyinv.T)
     a2 = torch.cholesky_solve(yt[:, None], torch.linalg.cholesky(Ky))[:, 0]
     assert float(((alpha - a2).abs() / a2.abs().max()).max()) <= 1e-6
+
+
+@pytest.mark.parametrize("N,D,ard", [(60, 1, False), (200, 3, True), (333, 6, False), (500, 12, True)])
+def test_marginal_likelihood_and_gradient(cuda_engine_ready, N, D, ard):
+    """cbo_obs_gp_nll against the host objective (GPy's formulas: obs_gp.neg_log_marginal_likelihood) and against a
+    central finite difference of the device objective itself."""
+    from cbo_with_oop_b200.obs_gp import DeviceObsGP, _device_objective, neg_log_marginal_likelihood
+    X, y, s2, ls = _data(2000 + N, N, D, ard)
+    theta = np.concatenate([[np.log(s2)], np.log(ls)])
+    ref, gref = neg_log_marginal_likelihood(theta, X, y, ard, 1e-2)
+    f = _device_objective(DeviceObsGP(X, y, 1e-2), ard)
+    nll, g = f(theta)
+    np.testing.assert_allclose(nll, ref, rtol=1e-9)
+    np.testing.assert_allclose(g, gref, rtol=1e-6, atol=1e-8 * np.abs(gref).max())
+    h = 1e-5
+    for k in range(len(theta)):
+        e = np.zeros_like(theta); e[k] = h
+        fd = (f(theta + e)[0] - f(theta - e)[0]) / (2 * h)
+        assert abs(fd - g[k]) <= 1e-5 * max(1.0, np.abs(g).max()), (k, fd, g[k])
+
+
+def test_hyperparameter_search_on_device_matches_host(cuda_engine_ready):
+    from cbo_with_oop_b200.obs_gp import optimize_hyperparameters
+    X, y, _, _ = _data(31, 250, 2)
+    floor = 0.5 * X.std(0)
+    host = optimize_hyperparameters(X, y, 1.0, 1.0, True, 1e-2, min_lengthscale=floor, max_variance=20.0)
+    dev = optimize_hyperparameters(X, y, 1.0, 1.0, True, 1e-2, min_lengthscale=floor, max_variance=20.0, device="cuda:0")
+    np.testing.assert_allclose(dev[0], host[0], rtol=1e-3)
+    np.testing.assert_allclose(dev[1], host[1], rtol=1e-3)
