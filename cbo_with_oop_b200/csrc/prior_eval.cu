@@ -104,8 +104,9 @@ struct PriorItem {
     bool split;      // a segment item
     bool partial;    // the item's row sums are partial (segments or folded column blocks): they go to the partial buffer
     __device__ __forceinline__ bool mine(int jb) const { const int r = jb % (2 * ns); return r == sp || r == 2 * ns - 1 - sp; }
-    __device__ __forceinline__ int kbeg(int jb) const { return split ? kt0 : 0; }
-    __device__ __forceinline__ int kend(int jb) const { return split ? kt1 : (jb + 1) * kKbPerJ; }
+    // SPLIT is a compile-time copy of `split` (kernel-uniform): the grid path keeps its loop bounds free of item state
+    template <bool SPLIT> __device__ __forceinline__ int kbeg(int jb) const { return SPLIT ? kt0 : 0; }
+    template <bool SPLIT> __device__ __forceinline__ int kend(int jb) const { return SPLIT ? kt1 : (jb + 1) * kKbPerJ; }
 };
 
 __device__ __forceinline__ PriorItem decode_prior_item(const cbo_set_desc* __restrict__ sets, int num_sets, PriorSplit split, int item) {
@@ -153,7 +154,7 @@ __device__ __forceinline__ void bar_consumers(int nthreads) { asm volatile("bar.
 
 // Consumer k loop + J-block epilogues of one work item for a warp whose first LIVE row blocks (of MA) hold live rows.
 // LIVE == 0: the warp owns only padding rows; it still walks the ring (wait full / arrive empty) so the counts match.
-template <class Cfg, int LIVE>
+template <class Cfg, int LIVE, bool SPLIT>
 __device__ __forceinline__ void consume_item(const PriorItem& it, const double* __restrict__ sA, const double* __restrict__ sB,
                                              double* __restrict__ sRed, uint64_t* full, uint64_t* empty, int& stage, unsigned& phase,
                                              const double* __restrict__ scratch, const double* __restrict__ w, int warp, int lane) {
@@ -166,7 +167,7 @@ __device__ __forceinline__ void consume_item(const PriorItem& it, const double* 
         for (int jb = it.jb0; jb < it.jb1; ++jb) {
             if (!it.mine(jb)) continue;
 #pragma unroll 1
-            for (int kt = it.kbeg(jb); kt < it.kend(jb); ++kt) {
+            for (int kt = it.template kbeg<SPLIT>(jb); kt < it.template kend<SPLIT>(jb); ++kt) {
                 mbar_wait(&full[stage], phase);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[stage]);
@@ -185,27 +186,35 @@ __device__ __forceinline__ void consume_item(const PriorItem& it, const double* 
 #pragma unroll 1
     for (int jb = it.jb0; jb < it.jb1; ++jb) {
         if (!it.mine(jb)) continue;
-        const int kb = it.kbeg(jb), ke = it.kend(jb), noff = jb * kKbPerJ;   // noff: first slab of the diagonal block
+        const int kb = it.template kbeg<SPLIT>(jb), ke = it.template kend<SPLIT>(jb), noff = jb * kKbPerJ;   // noff: first slab of the diagonal block
         auto double_acc = [&]() {   // strictly-lower blocks appear twice in u^T M u
 #pragma unroll
             for (int mi = 0; mi < LV; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < NB; ++ni) { acc[mi][ni][0] *= 2.0; acc[mi][ni][1] *= 2.0; }
         };
+        auto run = [&](int k0, int k1) {    // the steady state: wait full, 4 x (12 LDS.64 + 32 DMMA), arrive empty
 #pragma unroll 1
-        for (int kt = kb; kt < ke; ++kt) {
-            if (kt == noff && kt != kb) double_acc();
-            mbar_wait(&full[stage], phase);
-            mma_stage<BM, BN, MA, NB, LV>(sA + stage * Cfg::A_TILE, sB + stage * Cfg::B_TILE, acc, row0, col0, lane);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[stage]);
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            for (int kt = k0; kt < k1; ++kt) {
+                mbar_wait(&full[stage], phase);
+                mma_stage<BM, BN, MA, NB, LV>(sA + stage * Cfg::A_TILE, sB + stage * Cfg::B_TILE, acc, row0, col0, lane);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+        };
+        if constexpr (SPLIT) {
+            run(kb, ke);                     // a segment lies wholly below the diagonal block or is the diagonal block
+        } else {
+            run(kb, noff);                   // strictly-lower blocks ...
+            double_acc();                    // ... count twice (doubling the zeros of jb == 0 is harmless) ...
+            run(noff, ke);                   // ... the diagonal block once; the doubling stays out of the k loop
         }
         if (ke <= noff) double_acc();        // a split item's segment that lies wholly below the diagonal block
         const bool with_m = ke > noff;        // the segment holding the diagonal block also carries the block's share of u.w
         // J-block epilogue: q_g += sum_{j in J} T[g][j] u[g][j] ; m_g += sum_{j in J} u[g][j] w[j]
         // (u of column block jb sits in the scratch at slab jb*8 - ubase: a lower segment keeps it after its k slabs)
-        const int ubase = !it.split ? 0 : (ke <= noff ? noff - (ke - kb) : kb);
+        const int ubase = !SPLIT ? 0 : (ke <= noff ? noff - (ke - kb) : kb);
 #pragma unroll
         for (int mi = 0; mi < LV; ++mi) {
             const int r = row0 + mi * 8 + (lane >> 2);
@@ -215,13 +224,11 @@ __device__ __forceinline__ void consume_item(const PriorItem& it, const double* 
                 const int j = jb * BN + col0 + ni * 8 + (lane & 3) * 2;
                 const double2 u = __ldcg(reinterpret_cast<const double2*>(   // L2: never a stale L1 line of an earlier item
                     scratch + (size_t)((j >> 4) - ubase) * Cfg::A_TILE + frag_off(BM, (j & 15) >> 2, r, j & 3)));
+                const double2 ww = ldg_nc_d2(w + j);   // unconditional: the loads of the whole epilogue stay batched
                 q = fma(acc[mi][ni][0], u.x, q);
                 q = fma(acc[mi][ni][1], u.y, q);
-                if (with_m) {
-                    const double2 ww = ldg_nc_d2(w + j);
-                    mm = fma(u.x, ww.x, mm);
-                    mm = fma(u.y, ww.y, mm);
-                }
+                mm = fma(u.x, ww.x, mm);
+                mm = fma(u.y, ww.y, mm);
                 acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
             }
             q += __shfl_xor_sync(0xffffffffu, q, 1);
@@ -230,13 +237,13 @@ __device__ __forceinline__ void consume_item(const PriorItem& it, const double* 
             mm += __shfl_xor_sync(0xffffffffu, mm, 2);
             if ((lane & 3) == 0) {  // (wn, r) has exactly one owner: no race, fixed order -> deterministic
                 sRed[wn * BM + r] += q;
-                sRed[(WN + wn) * BM + r] += mm;
+                if (with_m) sRed[(WN + wn) * BM + r] += mm;
             }
         }
     }
 }
 
-template <class Cfg>
+template <class Cfg, bool SPLIT>
 __global__ void __launch_bounds__(Cfg::NT, 1)
 prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, PriorSplit split, int total_items,
                   int* __restrict__ counter, double* __restrict__ partials, double* __restrict__ scratch_base, size_t slot_doubles) {
@@ -284,7 +291,7 @@ prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, PriorSpli
 #pragma unroll 1
                 for (int jb = it.jb0; jb < it.jb1; ++jb) {
                     if (!it.mine(jb)) continue;
-                    const int kb = it.kbeg(jb), ke = it.kend(jb);
+                    const int kb = it.template kbeg<SPLIT>(jb), ke = it.template kend<SPLIT>(jb);
 #pragma unroll 1
                     for (int kt = kb; kt < ke; ++kt) {
                         mbar_wait(&empty[stage], phase ^ 1u);
@@ -312,8 +319,8 @@ prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, PriorSpli
             const int Npad = S.n_obs_pad;
             // 16-wide column slabs of U the item touches: all of them, or (split item) its k range [kt0, kt1) followed,
             // for a segment below the diagonal, by the 8 slabs of column block jb that the epilogue dots with
-            const int nk_item = it.split ? it.kt1 - it.kt0 : it.nJ * kKbPerJ;
-            const bool extra = it.split && it.kt1 <= it.jb0 * kKbPerJ;
+            const int nk_item = SPLIT ? it.kt1 - it.kt0 : it.nJ * kKbPerJ;
+            const bool extra = SPLIT && it.kt1 <= it.jb0 * kKbPerJ;
             const int nKT = nk_item + (extra ? kKbPerJ : 0);
             // live rows of this item (the last tile of a slice and the interventional rows fill only part of the 128):
             // rows past them are never generated, multiplied or stored (rows of U are independent in U*M)
@@ -358,7 +365,7 @@ prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, PriorSpli
                         if (u < units) {
                             const int ks = u / per_slab, wi = u - ks * per_slab, l = wi & 31;   // ks: slab inside the scratch
                             const int kb = l >> 3, half = l & 1, row = (wi >> 5) * 4 + ((l & 7) >> 1);
-                            const int kt = !it.split ? ks : (ks < nk_item ? it.kt0 + ks : it.jb0 * kKbPerJ + (ks - nk_item));
+                            const int kt = !SPLIT ? ks : (ks < nk_item ? it.kt0 + ks : it.jb0 * kKbPerJ + (ks - nk_item));
                             const int j = kt * kBK + kb * 4 + half * 2;
                             dst[x] = ks * Cfg::A_TILE + frag_off(BM, kb, row, half * 2);
                             if (sRow[CBO_MAX_D * BM + row]) {
@@ -384,7 +391,7 @@ prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, PriorSpli
             {   // live row blocks of THIS warp (warp-uniform), rounded up to an instantiated count
                 const int live_here = nlive - (warp / WN) * Cfg::MA * 8;
                 const int need = live_here <= 0 ? 0 : (live_here + 7) >> 3;
-#define CBO_CONSUME(LIVE) consume_item<Cfg, LIVE>(it, sA, sB, sRed, full, empty, stage, phase, scratch, S.w, warp, lane)
+#define CBO_CONSUME(LIVE) consume_item<Cfg, LIVE, SPLIT>(it, sA, sB, sRed, full, empty, stage, phase, scratch, S.w, warp, lane)
                 if (need >= 7) CBO_CONSUME(8);
                 else if (need == 6) CBO_CONSUME(6);
                 else if (need == 5) CBO_CONSUME(5);
@@ -531,10 +538,11 @@ int prior_eval_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int 
     unsigned char* ws = reinterpret_cast<unsigned char*>(d_ws);
     double* partials = reinterpret_cast<double*>(ws + kPriorWsHeader);
     double* scratch = partials + prior_partial_items(ctas) * kPartialDoubles;
-    auto kern = prior_eval_kernel<PriorCfgA>;
+    auto kern = split.chunk > 0 ? prior_eval_kernel<PriorCfgA, true> : prior_eval_kernel<PriorCfgA, false>;
     static bool configured = false;
     if (!configured) {
-        CBO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PriorCfgA::SMEM));
+        CBO_CUDA(cudaFuncSetAttribute(prior_eval_kernel<PriorCfgA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PriorCfgA::SMEM));
+        CBO_CUDA(cudaFuncSetAttribute(prior_eval_kernel<PriorCfgA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PriorCfgA::SMEM));
         configured = true;
     }
     CBO_CUDA(cudaMemsetAsync(d_ws, 0, kPriorWsHeader, st));

@@ -19,7 +19,7 @@
 //
 // Decomposition (no atomics, deterministic): grid = (k chunk, row block I of M, set x row pass).  A CTA owns the 128 rows
 // n of block I and a run of <= 32 of the block's 16-deep k slabs of M's lower block triangle (slabs left of the diagonal
-// block count twice), thread n accumulates s_n[r] = sum_k M[n][k] u_r[k] for up to 32 interventional rows r in
+// block count twice), streamed through a 3-stage shared-memory ring by TMA bulk copies; thread n accumulates s_n[r] = sum_k M[n][k] u_r[k] for up to 32 interventional rows r in
 // registers, then the CTA reduces sum_n u_r[n] s_n[r] and writes one (q, m) double-double partial per row;
 // prior_rows_finalize_kernel adds the partials in index order.
 #include "dmma_tile.cuh"
@@ -33,6 +33,8 @@ constexpr int kRowsPartial = 4;    // doubles per (item, row): q_hi, q_lo, m_hi,
 // arithmetic dominates), 4 for the row or two a post-intervention trial appends (6+ CTAs per SM: enough slabs in flight
 // to stream M at HBM speed)
 constexpr int kRowsWide = 32, kRowsNarrow = 4;
+constexpr int kRowsStages = 3;     // 16 KB slabs of M in flight per CTA (TMA bulk copies into a shared-memory ring)
+constexpr size_t kRowsRingBytes = (size_t)kRowsStages * kMBlkDoubles * sizeof(double);
 
 // error-free transformations; the intrinsics keep the compiler from contracting or re-associating them
 __device__ __forceinline__ void two_sum(double a, double b, double& s, double& e) {
@@ -87,6 +89,9 @@ prior_rows_kernel(const cbo_set_desc* __restrict__ sets, RowsShape sh, double* _
     const int diag0 = I * (kMBlkRows / kBK);                 // first slab of the diagonal block
     const double* __restrict__ U = S.u_int + (size_t)r0 * Npad;
 
+    extern __shared__ __align__(128) unsigned char ring_raw[];
+    double* sM = reinterpret_cast<double*>(ring_raw);        // [kRowsStages][128 x 16 slab, fragment order]
+    __shared__ uint64_t full[kRowsStages];
     __shared__ double su[2][RMAX][kBK];                      // u_r[k] of the current / next slab
     __shared__ double sred[kRowsThreads / 32][RMAX][kRowsPartial];
 
@@ -94,16 +99,22 @@ prior_rows_kernel(const cbo_set_desc* __restrict__ sets, RowsShape sh, double* _
 #pragma unroll
     for (int r = 0; r < RMAX; ++r) acc_s[r] = acc_c[r] = 0.0;
 
-    // this thread's row of a slab: 4 k4-groups of 32 bytes (consecutive threads -> consecutive 32-byte units)
-    auto load_row = [&](int kt, double (&dst)[kBK]) {
-        const double* slab = S.M + mblk_base(I, kt, Npad);
-#pragma unroll
-        for (int g = 0; g < kBK / 4; ++g) {
-            const double2 a = ldg_nc_d2(slab + ((g * kMBlkRows + tid) << 2));
-            const double2 b = ldg_nc_d2(slab + ((g * kMBlkRows + tid) << 2) + 2);
-            dst[4 * g] = a.x, dst[4 * g + 1] = a.y, dst[4 * g + 2] = b.x, dst[4 * g + 3] = b.y;
-        }
+    // M is streamed by TMA bulk copies (one contiguous 16 KB slab each, K1a's blocked layout) issued kRowsStages ahead by
+    // thread 0; the bytes in flight do not depend on the register budget, which is what an HBM-bound pass needs
+    const int nsl = kt1 - kt0;
+    auto issue = [&](int idx) {
+        const int st = idx % kRowsStages;
+        mbar_arrive_expect_tx(&full[st], (unsigned)(kMBlkDoubles * sizeof(double)));
+        bulk_g2s(sM + (size_t)st * kMBlkDoubles, S.M + mblk_base(I, kt0 + idx, Npad), (unsigned)(kMBlkDoubles * sizeof(double)), &full[st]);
     };
+    if (tid == 0) {
+        for (int st = 0; st < kRowsStages; ++st) mbar_init(&full[st], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int idx = 0; idx < kRowsStages && idx < nsl; ++idx) issue(idx);
+
     // this thread's share of a slab's u columns (R x 16 doubles over 128 threads)
     constexpr int UPT = (RMAX * kBK + kRowsThreads - 1) / kRowsThreads;
     auto load_u = [&](int kt, double (&dst)[UPT]) {
@@ -120,18 +131,24 @@ prior_rows_kernel(const cbo_set_desc* __restrict__ sets, RowsShape sh, double* _
             if (i < RMAX * kBK) su[buf][i / kBK][i % kBK] = src[x];
         }
     };
-    double mv[kBK], nx[kBK], un[UPT];
-    load_row(kt0, mv);
+    double un[UPT];
     load_u(kt0, un);
     store_u(0, un);
     __syncthreads();
 #pragma unroll 1
-    for (int kt = kt0; kt < kt1; ++kt) {
-        const int cur = (kt - kt0) & 1;
-        const bool more = kt + 1 < kt1;
-        if (more) {   // the next slab is in flight while this one is consumed
-            load_row(kt + 1, nx);
-            load_u(kt + 1, un);
+    for (int idx = 0; idx < nsl; ++idx) {
+        const int kt = kt0 + idx, cur = idx & 1, st = idx % kRowsStages;
+        const bool more = idx + 1 < nsl;
+        if (more) load_u(kt + 1, un);          // next slab's u columns in flight while this slab is consumed
+        mbar_wait(&full[st], (unsigned)(idx / kRowsStages) & 1u);
+        // this thread's row of the slab: 4 k4-groups of 32 bytes (consecutive threads -> consecutive 32-byte units)
+        double mv[kBK];
+        const double* slab = sM + (size_t)st * kMBlkDoubles;
+#pragma unroll
+        for (int g = 0; g < kBK / 4; ++g) {
+            const double2 a = *reinterpret_cast<const double2*>(slab + ((g * kMBlkRows + tid) << 2));
+            const double2 b = *reinterpret_cast<const double2*>(slab + ((g * kMBlkRows + tid) << 2) + 2);
+            mv[4 * g] = a.x, mv[4 * g + 1] = a.y, mv[4 * g + 2] = b.x, mv[4 * g + 3] = b.y;
         }
         if (kt < diag0) {   // strictly-lower blocks appear twice in u^T M u (exact scaling)
 #pragma unroll
@@ -144,12 +161,9 @@ prior_rows_kernel(const cbo_set_desc* __restrict__ sets, RowsShape sh, double* _
                 for (int k = 0; k < kBK; ++k) dot2_step(mv[k], su[cur][r][k], acc_s[r], acc_c[r]);
             }
         }
-        if (more) {
-            store_u(cur ^ 1, un);   // the other buffer was last read one iteration ago, before that iteration's barrier
-#pragma unroll
-            for (int k = 0; k < kBK; ++k) mv[k] = nx[k];
-        }
-        __syncthreads();
+        if (more) store_u(cur ^ 1, un);   // the other buffer was last read one iteration ago, before that iteration's barrier
+        __syncthreads();                   // every thread has read ring stage st and su[cur]
+        if (tid == 0 && idx + kRowsStages < nsl) issue(idx + kRowsStages);
     }
 
     // q partial of row r: sum over the block's rows n of u_r[n] * s_n[r]; m partial (once per row block: the CTA that
@@ -258,8 +272,14 @@ int prior_rows_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int 
     CBO_REQUIRE((long long)num_sets * sh.passes <= 65535, "cbo_prior_eval: too many sets for one launch");
     double* partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(d_ws) + ws_offset);
     const dim3 grid(sh.chunks, sh.nJ, num_sets * sh.passes);
-    if (sh.rmax == kRowsNarrow) prior_rows_kernel<kRowsNarrow><<<grid, kRowsThreads, 0, st>>>(d_sets, sh, partials);
-    else prior_rows_kernel<kRowsWide><<<grid, kRowsThreads, 0, st>>>(d_sets, sh, partials);
+    static bool configured = false;
+    if (!configured) {
+        CBO_CUDA(cudaFuncSetAttribute(prior_rows_kernel<kRowsNarrow>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowsRingBytes));
+        CBO_CUDA(cudaFuncSetAttribute(prior_rows_kernel<kRowsWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowsRingBytes));
+        configured = true;
+    }
+    if (sh.rmax == kRowsNarrow) prior_rows_kernel<kRowsNarrow><<<grid, kRowsThreads, kRowsRingBytes, st>>>(d_sets, sh, partials);
+    else prior_rows_kernel<kRowsWide><<<grid, kRowsThreads, kRowsRingBytes, st>>>(d_sets, sh, partials);
     note_launch();
     CBO_CUDA(cudaGetLastError());
     prior_rows_finalize_kernel<<<num_sets * sh.passes, dim3(32, sh.rmax), 0, st>>>(d_sets, sh, partials);
