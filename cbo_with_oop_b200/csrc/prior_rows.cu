@@ -141,24 +141,22 @@ prior_rows_kernel(const cbo_set_desc* __restrict__ sets, RowsShape sh, double* _
         const bool more = idx + 1 < nsl;
         if (more) load_u(kt + 1, un);          // next slab's u columns in flight while this slab is consumed
         mbar_wait(&full[st], (unsigned)(idx / kRowsStages) & 1u);
-        // this thread's row of the slab: 4 k4-groups of 32 bytes (consecutive threads -> consecutive 32-byte units)
-        double mv[kBK];
+        // this thread's row of the slab, one k4-group (32 bytes; consecutive threads -> consecutive 32-byte units) at a time:
+        // the group loop is NOT unrolled, so the fully unrolled body (RMAX rows x 4 products of ~10 instructions) stays
+        // inside the instruction cache -- unrolled over all 16 columns it was 37 % "no instruction" stalls
         const double* slab = sM + (size_t)st * kMBlkDoubles;
-#pragma unroll
+        const double scale = kt < diag0 ? 2.0 : 1.0;      // strictly-lower blocks appear twice in u^T M u (exact scaling)
+#pragma unroll 1
         for (int g = 0; g < kBK / 4; ++g) {
             const double2 a = *reinterpret_cast<const double2*>(slab + ((g * kMBlkRows + tid) << 2));
             const double2 b = *reinterpret_cast<const double2*>(slab + ((g * kMBlkRows + tid) << 2) + 2);
-            mv[4 * g] = a.x, mv[4 * g + 1] = a.y, mv[4 * g + 2] = b.x, mv[4 * g + 3] = b.y;
-        }
-        if (kt < diag0) {   // strictly-lower blocks appear twice in u^T M u (exact scaling)
+            const double mv[4] = {a.x * scale, a.y * scale, b.x * scale, b.y * scale};
 #pragma unroll
-            for (int k = 0; k < kBK; ++k) mv[k] *= 2.0;
-        }
+            for (int r = 0; r < RMAX; ++r) {
+                if (r < R) {
 #pragma unroll
-        for (int r = 0; r < RMAX; ++r) {
-            if (r < R) {
-#pragma unroll
-                for (int k = 0; k < kBK; ++k) dot2_step(mv[k], su[cur][r][k], acc_s[r], acc_c[r]);
+                    for (int k = 0; k < 4; ++k) dot2_step(mv[k], su[cur][r][g * 4 + k], acc_s[r], acc_c[r]);
+                }
             }
         }
         if (more) store_u(cur ^ 1, un);   // the other buffer was last read one iteration ago, before that iteration's barrier
