@@ -154,7 +154,7 @@ def run_reference(args, world, rank):
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "CPU restatement of the reference's arithmetic (oracle/cbo_oracle.py, factorised vectorised form) on the "
                     "host cores; the reference itself needs GPy/emukit/paramz, which cannot be installed offline"}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -190,6 +190,17 @@ class ClockSampler(threading.Thread):
         busy = [s for s in sm if s > 0.5 * (max(mx) if mx else 1)]
         return {"sm_mhz": float(np.median(busy or sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# stdout carries exactly ONE line, the JSON record: the process-wide fd 1 is pointed at stderr before any library loads
+# (NCCL prints its version banner to fd 1 from C), and the record goes to a private duplicate of the original stdout.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
 
 
 def run_ours(args, world, rank, local_rank):
@@ -356,7 +367,7 @@ def run_ours(args, world, rank, local_rank):
                           % (r["sample_points"], G_set),
                 "one_off_s": r["one_off_s"], "per_point_s": r["per_point_s"], "host_cores": r["cores"],
                 "reference_faithful_direct_form": r.get("direct_form")}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
