@@ -36,13 +36,19 @@ void note_launch(int n = 1);
 // does the library compute the causal prior of this set (as opposed to non-causal sets / caller-supplied priors)?
 __host__ __device__ inline bool computes_prior(const cbo_set_desc& S) { return S.causal && !S.prior_external; }
 
-// Work-item kinds of the batched kernels.  Every batched launch is a flat list of items
-// (set 0 tiles, set 1 tiles, ...); host and device count them with the same function.
-enum { kItemsPriorGrid = 0, kItemsPriorTrain = 1, kItemsSweep = 2 };
-__host__ __device__ inline long long host_items(const cbo_set_desc& S, int kind) {
-    if (kind == kItemsPriorGrid) return computes_prior(S) ? (S.g_count + CBO_PRIOR_TILE - 1) / CBO_PRIOR_TILE : 0;
-    if (kind == kItemsPriorTrain) return computes_prior(S) ? (S.n_int + CBO_PRIOR_TILE - 1) / CBO_PRIOR_TILE : 0;
+// Work items of the batched sweep kernel.  A batched launch is a flat list of items (set 0 tiles, set 1 tiles, ...);
+// host and device count them with the same function.
+enum { kItemsSweep = 2 };
+__host__ __device__ inline long long host_items(const cbo_set_desc& S, int /*kind*/) {
     return (S.g_count + CBO_SWEEP_TILE - 1) / CBO_SWEEP_TILE;
+}
+
+// Opt a kernel into `bytes` of dynamic shared memory.  Called before every launch that needs more than 48 KB: the
+// attribute is per device and per context, the call costs about a microsecond, and keeping no "already configured" flag
+// keeps the library free of hidden state (several devices or threads in one process stay correct).
+template <class K>
+inline cudaError_t allow_dynamic_smem(K kernel, size_t bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
 // ---- device helpers --------------------------------------------------------------------------------

@@ -359,16 +359,12 @@ int obs_gp_fit_impl(const cbo_set_desc* h_sets, int num_sets, double jitter, voi
                     cudaStream_t st) {
     constexpr size_t TILE_SMEM = (size_t)kFitStages * 2 * kFB * kBK * sizeof(double);
     constexpr size_t DIAG_SMEM = ((size_t)kFB * kDiagLd + kFB) * sizeof(double);
-    static bool configured = false;
-    if (!configured) {
-        CBO_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
-        CBO_CUDA(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
-        CBO_CUDA(cudaFuncSetAttribute(syrk_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
-        CBO_CUDA(cudaFuncSetAttribute(winv_scale_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
-        CBO_CUDA(cudaFuncSetAttribute(winv_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
-        CBO_CUDA(cudaFuncSetAttribute(kyinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
-        configured = true;
-    }
+    CBO_CUDA(allow_dynamic_smem(potrf_diag_kernel, DIAG_SMEM));
+    CBO_CUDA(allow_dynamic_smem(trsm_panel_kernel, TILE_SMEM));
+    CBO_CUDA(allow_dynamic_smem(syrk_update_kernel, TILE_SMEM));
+    CBO_CUDA(allow_dynamic_smem(winv_scale_kernel, TILE_SMEM));
+    CBO_CUDA(allow_dynamic_smem(winv_update_kernel, TILE_SMEM));
+    CBO_CUDA(allow_dynamic_smem(kyinv_kernel, TILE_SMEM));
     CBO_REQUIRE(d_info != nullptr, "cbo_obs_gp_fit: d_info is NULL");
     for (int s = 0; s < num_sets; ++s) {
         const cbo_set_desc& S = h_sets[s];

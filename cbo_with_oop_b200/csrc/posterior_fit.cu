@@ -131,11 +131,7 @@ int posterior_fit_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, i
         if (S.n_int > nmax) nmax = S.n_int;
     }
     const size_t smem = ((size_t)nmax * nmax + 2 * (size_t)nmax + (size_t)nmax * CBO_MAX_D) * sizeof(double);
-    static size_t configured = 0;
-    if (smem > configured) {
-        CBO_CUDA(cudaFuncSetAttribute(posterior_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    if (smem > 48 * 1024) CBO_CUDA(allow_dynamic_smem(posterior_fit_kernel, smem));
     posterior_fit_kernel<<<num_sets, kFitThreads, smem, st>>>(d_sets);
     note_launch();
     CBO_CUDA(cudaGetLastError());

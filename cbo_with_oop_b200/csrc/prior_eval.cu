@@ -152,12 +152,77 @@ __device__ __forceinline__ PriorItem decode_prior_item(const cbo_set_desc* __res
 __device__ __forceinline__ void bar_all(int nthreads) { asm volatile("bar.sync 0, %0;" ::"r"(nthreads) : "memory"); }
 __device__ __forceinline__ void bar_consumers(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 
+// The LAST column block of M when few of its 128 columns are live (n_obs = 128 (nJ - 1) + Lc with Lc <= 64; config 5 has
+// Lc = 16).  In the regular warp tiling only the warps that own the live columns would do useful DMMAs while the block
+// still costs a full 1/nJ-th of the item's longest k loop (2.5 % of an item at nJ = 79).  Here the 8 consumer warps are
+// re-tiled over (128 rows) x (NW * NB2 * 8 live columns): MW x NW warps of MA2 x NB2 blocks each, so the block costs
+// Lc/128 of a full one (it then runs at the speed the slabs arrive).  Same ring protocol: every warp waits on every
+// stage and arrives once.
+template <class Cfg, int MW, int NW, int MA2, int NB2>
+__device__ __forceinline__ void consume_ragged_block(const PriorItem& it, const double* __restrict__ sA, const double* __restrict__ sB,
+                                                     double* __restrict__ sRed, uint64_t* full, uint64_t* empty, int& stage,
+                                                     unsigned& phase, const double* __restrict__ scratch, const double* __restrict__ w,
+                                                     int warp, int lane) {
+    constexpr int BM = Cfg::BM, BN = Cfg::BN, WN = Cfg::WN, STAGES = Cfg::STAGES;
+    static_assert(MW * NW * 32 == Cfg::NCONS && MW * MA2 * 8 == BM && NW <= WN, "re-tiling must cover the 128 rows with all consumer warps");
+    const int jb = it.nJ - 1, noff = jb * kKbPerJ, ke = (jb + 1) * kKbPerJ;
+    const int row0 = (warp / NW) * MA2 * 8, wn2 = warp % NW, col0 = wn2 * NB2 * 8;
+    double acc[MA2][NB2][2];
+#pragma unroll
+    for (int mi = 0; mi < MA2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NB2; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    auto run = [&](int k0, int k1) {
+#pragma unroll 1
+        for (int kt = k0; kt < k1; ++kt) {
+            mbar_wait(&full[stage], phase);
+            mma_stage<BM, BN, MA2, NB2, MA2>(sA + stage * Cfg::A_TILE, sB + stage * Cfg::B_TILE, acc, row0, col0, lane);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+    };
+    run(0, noff);
+#pragma unroll
+    for (int mi = 0; mi < MA2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NB2; ++ni) { acc[mi][ni][0] *= 2.0; acc[mi][ni][1] *= 2.0; }
+    run(noff, ke);
+    // the row sums of this block go into slots that other warps own in the regular tiling: wait until every consumer
+    // warp is past its earlier epilogues (the producer takes no part in barrier 1)
+    bar_consumers(Cfg::NCONS);
+#pragma unroll
+    for (int mi = 0; mi < MA2; ++mi) {
+        const int r = row0 + mi * 8 + (lane >> 2);
+        double q = 0.0, mm = 0.0;
+#pragma unroll
+        for (int ni = 0; ni < NB2; ++ni) {
+            const int j = jb * BN + col0 + ni * 8 + (lane & 3) * 2;
+            const double2 u = __ldcg(reinterpret_cast<const double2*>(scratch + (size_t)(j >> 4) * Cfg::A_TILE + frag_off(BM, (j & 15) >> 2, r, j & 3)));
+            const double2 ww = ldg_nc_d2(w + j);
+            q = fma(acc[mi][ni][0], u.x, q);
+            q = fma(acc[mi][ni][1], u.y, q);
+            mm = fma(u.x, ww.x, mm);
+            mm = fma(u.y, ww.y, mm);
+        }
+        q += __shfl_xor_sync(0xffffffffu, q, 1);
+        q += __shfl_xor_sync(0xffffffffu, q, 2);
+        mm += __shfl_xor_sync(0xffffffffu, mm, 1);
+        mm += __shfl_xor_sync(0xffffffffu, mm, 2);
+        if ((lane & 3) == 0) {  // (wn2, r) has exactly one owner in this tiling
+            sRed[wn2 * BM + r] += q;
+            sRed[(WN + wn2) * BM + r] += mm;
+        }
+    }
+}
+
 // Consumer k loop + J-block epilogues of one work item for a warp whose first LIVE row blocks (of MA) hold live rows.
 // LIVE == 0: the warp owns only padding rows; it still walks the ring (wait full / arrive empty) so the counts match.
 template <class Cfg, int LIVE, bool SPLIT>
 __device__ __forceinline__ void consume_item(const PriorItem& it, const double* __restrict__ sA, const double* __restrict__ sB,
                                              double* __restrict__ sRed, uint64_t* full, uint64_t* empty, int& stage, unsigned& phase,
-                                             const double* __restrict__ scratch, const double* __restrict__ w, int warp, int lane) {
+                                             const double* __restrict__ scratch, const double* __restrict__ w, int warp, int lane,
+                                             int ragged_cols) {
     constexpr int BM = Cfg::BM, BN = Cfg::BN, MA = Cfg::MA, NB = Cfg::NB, WN = Cfg::WN, STAGES = Cfg::STAGES;
     static_assert(BN / kBK == kKbPerJ, "J block width");
     const int wm = warp / WN, wn = warp % WN;
@@ -183,8 +248,10 @@ __device__ __forceinline__ void consume_item(const PriorItem& it, const double* 
 #pragma unroll
         for (int ni = 0; ni < NB; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
+    // full tiles of the grid path hand the last column block to consume_ragged_block when at most 64 of its columns are live
+    const int jend = (!SPLIT && LIVE == MA && ragged_cols > 0) ? it.nJ - 1 : it.jb1;
 #pragma unroll 1
-    for (int jb = it.jb0; jb < it.jb1; ++jb) {
+    for (int jb = it.jb0; jb < jend; ++jb) {
         if (!it.mine(jb)) continue;
         const int kb = it.template kbeg<SPLIT>(jb), ke = it.template kend<SPLIT>(jb), noff = jb * kKbPerJ;   // noff: first slab of the diagonal block
         auto double_acc = [&]() {   // strictly-lower blocks appear twice in u^T M u
@@ -240,6 +307,11 @@ __device__ __forceinline__ void consume_item(const PriorItem& it, const double* 
                 if (with_m) sRed[(WN + wn) * BM + r] += mm;
             }
         }
+    }
+    if constexpr (!SPLIT && LIVE == MA) {
+        if (ragged_cols > 32) consume_ragged_block<Cfg, 4, 2, 4, 4>(it, sA, sB, sRed, full, empty, stage, phase, scratch, w, warp, lane);
+        else if (ragged_cols > 16) consume_ragged_block<Cfg, 8, 1, 2, 4>(it, sA, sB, sRed, full, empty, stage, phase, scratch, w, warp, lane);
+        else if (ragged_cols > 0) consume_ragged_block<Cfg, 8, 1, 2, 2>(it, sA, sB, sRed, full, empty, stage, phase, scratch, w, warp, lane);
     }
 }
 
@@ -391,7 +463,12 @@ prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, PriorSpli
             {   // live row blocks of THIS warp (warp-uniform), rounded up to an instantiated count
                 const int live_here = nlive - (warp / WN) * Cfg::MA * 8;
                 const int need = live_here <= 0 ? 0 : (live_here + 7) >> 3;
-#define CBO_CONSUME(LIVE) consume_item<Cfg, LIVE, SPLIT>(it, sA, sB, sRed, full, empty, stage, phase, scratch, S.w, warp, lane)
+                // live columns of the last column block when they are few (<= 64) and the item is a full tile of a grid
+                // launch with more than one column block; 0 = regular tiling throughout.  CTA-uniform: every consumer
+                // warp of a full tile runs the LIVE == MA instantiation.
+                const int lc = S.n_obs - (it.nJ - 1) * BN;
+                const int ragged_cols = (!SPLIT && nlive == BM && it.nJ > 1 && lc <= 64) ? lc : 0;
+#define CBO_CONSUME(LIVE) consume_item<Cfg, LIVE, SPLIT>(it, sA, sB, sRed, full, empty, stage, phase, scratch, S.w, warp, lane, ragged_cols)
                 if (need >= 7) CBO_CONSUME(8);
                 else if (need == 6) CBO_CONSUME(6);
                 else if (need == 5) CBO_CONSUME(5);
@@ -539,12 +616,8 @@ int prior_eval_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int 
     double* partials = reinterpret_cast<double*>(ws + kPriorWsHeader);
     double* scratch = partials + prior_partial_items(ctas) * kPartialDoubles;
     auto kern = split.chunk > 0 ? prior_eval_kernel<PriorCfgA, true> : prior_eval_kernel<PriorCfgA, false>;
-    static bool configured = false;
-    if (!configured) {
-        CBO_CUDA(cudaFuncSetAttribute(prior_eval_kernel<PriorCfgA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PriorCfgA::SMEM));
-        CBO_CUDA(cudaFuncSetAttribute(prior_eval_kernel<PriorCfgA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PriorCfgA::SMEM));
-        configured = true;
-    }
+    CBO_CUDA(allow_dynamic_smem(prior_eval_kernel<PriorCfgA, true>, PriorCfgA::SMEM));
+    CBO_CUDA(allow_dynamic_smem(prior_eval_kernel<PriorCfgA, false>, PriorCfgA::SMEM));
     CBO_CUDA(cudaMemsetAsync(d_ws, 0, kPriorWsHeader, st));
     kern<<<(unsigned)grid, PriorCfgA::NT, PriorCfgA::SMEM, st>>>(d_sets, num_sets, split, (int)total,
                                                                  reinterpret_cast<int*>(ws), partials, scratch, slot);

@@ -126,11 +126,7 @@ int prior_precompute_impl(const cbo_set_desc* h_sets, int num_sets, cudaStream_t
     constexpr int STAGES = 4;
     constexpr size_t SMEM = (size_t)STAGES * 2 * CBO_NPAD * kBK * sizeof(double);
     auto kern = syrk_kernel<2, 4, 8, 4, STAGES>;
-    static bool configured = false;
-    if (!configured) {
-        CBO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-        configured = true;
-    }
+    CBO_CUDA(allow_dynamic_smem(kern, SMEM));
     for (int s = 0; s < num_sets; ++s) {
         const cbo_set_desc& S = h_sets[s];
         if (!computes_prior(S)) continue;

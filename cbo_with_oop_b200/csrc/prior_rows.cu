@@ -270,12 +270,8 @@ int prior_rows_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int 
     CBO_REQUIRE((long long)num_sets * sh.passes <= 65535, "cbo_prior_eval: too many sets for one launch");
     double* partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(d_ws) + ws_offset);
     const dim3 grid(sh.chunks, sh.nJ, num_sets * sh.passes);
-    static bool configured = false;
-    if (!configured) {
-        CBO_CUDA(cudaFuncSetAttribute(prior_rows_kernel<kRowsNarrow>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowsRingBytes));
-        CBO_CUDA(cudaFuncSetAttribute(prior_rows_kernel<kRowsWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowsRingBytes));
-        configured = true;
-    }
+    CBO_CUDA(allow_dynamic_smem(prior_rows_kernel<kRowsNarrow>, kRowsRingBytes));
+    CBO_CUDA(allow_dynamic_smem(prior_rows_kernel<kRowsWide>, kRowsRingBytes));
     if (sh.rmax == kRowsNarrow) prior_rows_kernel<kRowsNarrow><<<grid, kRowsThreads, kRowsRingBytes, st>>>(d_sets, sh, partials);
     else prior_rows_kernel<kRowsWide><<<grid, kRowsThreads, kRowsRingBytes, st>>>(d_sets, sh, partials);
     note_launch();

@@ -298,11 +298,7 @@ int sweep_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_s
     if (total > 0) {
         const size_t smem = ((size_t)nmax * (nmax + 1) / 2 + 2 * (size_t)nmax + (size_t)nmax * CBO_MAX_D +
                              (nmax > 48 ? (size_t)nmax * kSweepThreads : 0)) * sizeof(double);
-        static size_t configured = 0;
-        if (smem > configured) {
-            CBO_CUDA(cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
-        }
+        if (smem > 48 * 1024) CBO_CUDA(allow_dynamic_smem(sweep_kernel, smem));
         sweep_kernel<<<(unsigned)total, kSweepThreads, smem, st>>>(d_sets, num_sets, best, (double)task_sign, d_tile_best);
         note_launch();
         CBO_CUDA(cudaGetLastError());

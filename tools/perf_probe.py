@@ -17,7 +17,6 @@ ap.add_argument("--c", type=int, default=3)
 ap.add_argument("--variant", type=int, default=0)
 ap.add_argument("--reps", type=int, default=3)
 args = ap.parse_args()
-os.environ["CBO_PRIOR_VARIANT"] = str(args.variant)
 
 import numpy as np
 import torch
