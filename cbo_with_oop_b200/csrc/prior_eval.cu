@@ -22,7 +22,10 @@
 //   (warps 0-7)             never touch global memory inside the k loop; after each J block a short epilogue dots the
 //                           accumulators with u (re-read from the scratch) and w.  Warps whose rows are partly or wholly
 //                           padding (last tile of a slice, small explicit-point batches) run instantiations with fewer
-//                           live row blocks.
+//                           live row blocks; a last column block with few live columns (N = 128 k + Lc, Lc <= 64) is
+//                           consumed with all warps re-tiled over those columns (consume_ragged_block).
+// Launches with too few tiles to fill the GPU (explicit points, small grids) are cut into segments of M's triangle
+// (template SPLIT); the interventional rows (cbo_prior_eval which == 1) are evaluated by prior_rows.cu.
 // Roofline: FP64 pipe.  Executed flops per candidate = N^2 (+ lower order); the dense-counted figure of
 // SURVEY.md §8(d) is 2 N^2 + 2 N + d N.  Scratch traffic: each U slab is re-read once per J block
 // (~N/256 times), about 1 TB/s of L2/HBM reads chip-wide at N = 1e4 -- 15 % of HBM bandwidth.
