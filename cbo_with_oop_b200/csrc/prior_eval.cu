@@ -403,15 +403,29 @@ prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, PriorSpli
             const int nlive = left < BM ? (int)left : BM;
 
             // per-row table offsets (C-order decomposition of the flat grid index, last dim fastest)
+            const bool small_grid = S.g_total < 0x7fffffffLL;   // 32-bit index arithmetic (64-bit div/mod is a long emulated sequence)
             for (int r = tid; r < BM; r += NCONS) {
                 const bool live = r < nlive;
-                long long gg = gbeg + (live ? (long long)it.tile * BM + r : 0);
+                const long long g0 = gbeg + (live ? (long long)it.tile * BM + r : 0);
+                if (small_grid) {
+                    unsigned gg = (unsigned)g0;
 #pragma unroll
-                for (int k = CBO_MAX_D - 1; k >= 0; --k) {
-                    if (k < d) {
-                        const long long pk = S.points ? S.g_total : (long long)S.p[k];
-                        sRow[k * BM + r] = (int)(gg % pk) * Npad;
-                        gg /= pk;
+                    for (int k = CBO_MAX_D - 1; k >= 0; --k) {
+                        if (k < d) {
+                            const unsigned pk = S.points ? (unsigned)S.g_total : (unsigned)S.p[k], q = gg / pk;
+                            sRow[k * BM + r] = (int)(gg - q * pk) * Npad;
+                            gg = q;
+                        }
+                    }
+                } else {
+                    long long gg = g0;
+#pragma unroll
+                    for (int k = CBO_MAX_D - 1; k >= 0; --k) {
+                        if (k < d) {
+                            const long long pk = S.points ? S.g_total : (long long)S.p[k];
+                            sRow[k * BM + r] = (int)(gg % pk) * Npad;
+                            gg /= pk;
+                        }
                     }
                 }
                 sRow[CBO_MAX_D * BM + r] = live ? 1 : 0;
@@ -425,39 +439,46 @@ prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, PriorSpli
 #pragma unroll
                 for (int k = 0; k < CBO_MAX_D; ++k) tab[k] = S.tab[k < d ? k : 0];
                 // unit = one 16-byte pair of one row; a warp's 32 units are 4 rows x 128 bytes of one slab: the table
-                // reads are four full lines and the scratch writes four full lines.
+                // reads are four full lines and the scratch writes four full lines.  A thread owns the SAME (row, k pair)
+                // positions in every slab, so its row offsets, live flags and scratch offsets are set up once per item and
+                // the slab loop is loads, multiplies and a store -- no index arithmetic, no division.
                 const int per_slab = ((nlive + 3) >> 2) * 32;   // 16-byte units of the live rows in one slab
-                const int units = nKT * per_slab;
-                constexpr int UNROLL = 4;
-                for (int u0 = tid; u0 < units; u0 += NCONS * UNROLL) {
-                    double2 v[UNROLL];
-                    int dst[UNROLL];
+                constexpr int UW = (BM / 4 * 32 + NCONS - 1) / NCONS;
+                int roff[UW][CBO_MAX_D], dst0[UW], j0[UW];
+                bool valid[UW], live[UW];
 #pragma unroll
-                    for (int x = 0; x < UNROLL; ++x) {
-                        const int u = u0 + x * NCONS;
+                for (int x = 0; x < UW; ++x) {
+                    const int wi = tid + x * NCONS, l = wi & 31;
+                    const int kb = l >> 3, half = l & 1, row = (wi >> 5) * 4 + ((l & 7) >> 1);
+                    valid[x] = wi < per_slab;
+                    live[x] = valid[x] && sRow[CBO_MAX_D * BM + row] != 0;
+                    j0[x] = kb * 4 + half * 2;
+                    dst0[x] = frag_off(BM, kb, row, half * 2);
+#pragma unroll
+                    for (int k = 0; k < CBO_MAX_D; ++k) roff[x][k] = (k < d && valid[x]) ? sRow[k * BM + row] : 0;
+                }
+#pragma unroll 1
+                for (int ks = 0; ks < nKT; ++ks) {                  // ks: slab inside the scratch
+                    const int kt = !SPLIT ? ks : (ks < nk_item ? it.kt0 + ks : it.jb0 * kKbPerJ + (ks - nk_item));
+                    double2 v[UW];
+#pragma unroll
+                    for (int x = 0; x < UW; ++x) {
                         v[x] = make_double2(0.0, 0.0);
-                        dst[x] = -1;
-                        if (u < units) {
-                            const int ks = u / per_slab, wi = u - ks * per_slab, l = wi & 31;   // ks: slab inside the scratch
-                            const int kb = l >> 3, half = l & 1, row = (wi >> 5) * 4 + ((l & 7) >> 1);
-                            const int kt = !SPLIT ? ks : (ks < nk_item ? it.kt0 + ks : it.jb0 * kKbPerJ + (ks - nk_item));
-                            const int j = kt * kBK + kb * 4 + half * 2;
-                            dst[x] = ks * Cfg::A_TILE + frag_off(BM, kb, row, half * 2);
-                            if (sRow[CBO_MAX_D * BM + row]) {
-                                v[x] = ldg_nc_d2(tab[0] + sRow[row] + j);
+                        if (live[x]) {
+                            const int j = kt * kBK + j0[x];
+                            v[x] = ldg_nc_d2(tab[0] + roff[x][0] + j);
 #pragma unroll
-                                for (int k = 1; k < CBO_MAX_D; ++k) {
-                                    if (k < d) {
-                                        const double2 t = ldg_nc_d2(tab[k] + sRow[k * BM + row] + j);
-                                        v[x].x *= t.x; v[x].y *= t.y;
-                                    }
+                            for (int k = 1; k < CBO_MAX_D; ++k) {
+                                if (k < d) {
+                                    const double2 t = ldg_nc_d2(tab[k] + roff[x][k] + j);
+                                    v[x].x *= t.x; v[x].y *= t.y;
                                 }
                             }
                         }
                     }
 #pragma unroll
-                    for (int x = 0; x < UNROLL; ++x)
-                        if (dst[x] >= 0) *reinterpret_cast<double2*>(scratch + dst[x]) = v[x];
+                    for (int x = 0; x < UW; ++x)
+                        if (valid[x]) *reinterpret_cast<double2*>(scratch + (size_t)ks * Cfg::A_TILE + dst0[x]) = v[x];
                 }
                 fence_proxy_async();  // generic-proxy writes above -> visible to the TMA (async proxy) reads below
             }
