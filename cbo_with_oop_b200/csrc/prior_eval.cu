@@ -112,13 +112,27 @@ struct PriorItem {
     template <bool SPLIT> __device__ __forceinline__ int kend(int jb) const { return SPLIT ? kt1 : (jb + 1) * kKbPerJ; }
 };
 
-__device__ __forceinline__ PriorItem decode_prior_item(const cbo_set_desc* __restrict__ sets, int num_sets, PriorSplit split, int item) {
+// First work item of every set, computed on the host and passed as a kernel parameter: finding an item's set is a scan
+// over constants instead of a walk over the descriptors in global memory (which cost 5 us per item with coral's 25 sets --
+// as much as a quarter of a 128-column item's DMMA time).  Launches with more sets than fit fall back to the walk.
+constexpr int kMaxBases = 32;
+struct PriorBases { int n; int base[kMaxBases + 1]; };
+
+__device__ __forceinline__ PriorItem decode_prior_item(const cbo_set_desc* __restrict__ sets, int num_sets, PriorSplit split,
+                                                       const PriorBases& pb, int item) {
     const int chunk = split.chunk;
     int local = item, s = 0;
-    for (; s < num_sets - 1; ++s) {
-        const int cnt = (int)prior_items(sets[s], split);
-        if (local < cnt) break;
-        local -= cnt;
+    if (pb.n == num_sets) {
+#pragma unroll 1
+        for (; s < num_sets - 1; ++s)
+            if (item < pb.base[s + 1]) break;
+        local = item - pb.base[s];
+    } else {
+        for (; s < num_sets - 1; ++s) {
+            const int cnt = (int)prior_items(sets[s], split);
+            if (local < cnt) break;
+            local -= cnt;
+        }
     }
     PriorItem it;
     it.S = sets + s;
@@ -320,7 +334,7 @@ __device__ __forceinline__ void consume_item(const PriorItem& it, const double* 
 
 template <class Cfg, bool SPLIT>
 __global__ void __launch_bounds__(Cfg::NT, 1)
-prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, PriorSplit split, int total_items,
+prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, PriorSplit split, const PriorBases pb, int total_items,
                   int* __restrict__ counter, double* __restrict__ partials, double* __restrict__ scratch_base, size_t slot_doubles) {
     constexpr int BM = Cfg::BM, BN = Cfg::BN, WN = Cfg::WN, NT = Cfg::NT, NCONS = Cfg::NCONS;
     constexpr int STAGES = Cfg::STAGES;
@@ -358,7 +372,7 @@ prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, PriorSpli
         for (;;) {
             const int item = *sItem;                                   // barrier A happened (kernel start / end of last item)
             if (item >= total_items) break;
-            const PriorItem it = decode_prior_item(sets, num_sets, split, item);
+            const PriorItem it = decode_prior_item(sets, num_sets, split, pb, item);
             const double* __restrict__ M = it.S->M;
             const int Npad = it.S->n_obs_pad;
             bar_all(NT);                                               // B
@@ -386,7 +400,7 @@ prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, PriorSpli
         for (;;) {
             const int item = *sItem;
             if (item >= total_items) break;
-            const PriorItem it = decode_prior_item(sets, num_sets, split, item);
+            const PriorItem it = decode_prior_item(sets, num_sets, split, pb, item);
             const cbo_set_desc& S = *it.S;
             // effective problem: the tensor grid, or explicit points (one table with a row per candidate)
             const int d = S.points ? 1 : S.d;
@@ -643,7 +657,12 @@ int prior_eval_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int 
     CBO_CUDA(allow_dynamic_smem(prior_eval_kernel<PriorCfgA, true>, PriorCfgA::SMEM));
     CBO_CUDA(allow_dynamic_smem(prior_eval_kernel<PriorCfgA, false>, PriorCfgA::SMEM));
     CBO_CUDA(cudaMemsetAsync(d_ws, 0, kPriorWsHeader, st));
-    kern<<<(unsigned)grid, PriorCfgA::NT, PriorCfgA::SMEM, st>>>(d_sets, num_sets, split, (int)total,
+    PriorBases pb;
+    pb.n = num_sets <= kMaxBases ? num_sets : 0;
+    pb.base[0] = 0;
+    for (int s = 0; s < kMaxBases; ++s)
+        pb.base[s + 1] = pb.base[s] + (s < pb.n ? (int)prior_items(h_sets[s], split) : 0);
+    kern<<<(unsigned)grid, PriorCfgA::NT, PriorCfgA::SMEM, st>>>(d_sets, num_sets, split, pb, (int)total,
                                                                  reinterpret_cast<int*>(ws), partials, scratch, slot);
     note_launch();
     CBO_CUDA(cudaGetLastError());
