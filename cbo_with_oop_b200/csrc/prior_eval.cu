@@ -104,12 +104,18 @@ struct PriorCfg {
 struct PriorItem {
     const cbo_set_desc* S;
     int tile, nJ, jb0, jb1, kt0, kt1, sp, ns;
+    int kmax;        // 16-deep k slabs that hold live rows of M: ceil(n_obs / 16); the slabs past them are zero padding
     bool split;      // a segment item
     bool partial;    // the item's row sums are partial (segments or folded column blocks): they go to the partial buffer
     __device__ __forceinline__ bool mine(int jb) const { const int r = jb % (2 * ns); return r == sp || r == 2 * ns - 1 - sp; }
     // SPLIT is a compile-time copy of `split` (kernel-uniform): the grid path keeps its loop bounds free of item state
     template <bool SPLIT> __device__ __forceinline__ int kbeg(int jb) const { return SPLIT ? kt0 : 0; }
-    template <bool SPLIT> __device__ __forceinline__ int kend(int jb) const { return SPLIT ? kt1 : (jb + 1) * kKbPerJ; }
+    // end of the k loop: padding slabs are skipped by the producer and the consumers alike (U and M are exactly zero there,
+    // so nothing changes but the stage count: 7 instead of 8 at N = 100); phase 1 still fills them for the epilogue's reads
+    template <bool SPLIT> __device__ __forceinline__ int kend(int jb) const {
+        const int e = SPLIT ? kt1 : (jb + 1) * kKbPerJ;
+        return e < kmax ? e : kmax;
+    }
 };
 
 // First work item of every set, computed on the host and passed as a kernel parameter: finding an item's set is a scan
@@ -137,6 +143,7 @@ __device__ __forceinline__ PriorItem decode_prior_item(const cbo_set_desc* __res
     PriorItem it;
     it.S = sets + s;
     it.nJ = prior_nJ(sets[s]);
+    it.kmax = (sets[s].n_obs + kBK - 1) / kBK;
     it.split = chunk > 0;
     it.sp = 0, it.ns = 1;
     if (!it.split) {
@@ -182,7 +189,7 @@ __device__ __forceinline__ void consume_ragged_block(const PriorItem& it, const 
                                                      int warp, int lane) {
     constexpr int BM = Cfg::BM, BN = Cfg::BN, WN = Cfg::WN, STAGES = Cfg::STAGES;
     static_assert(MW * NW * 32 == Cfg::NCONS && MW * MA2 * 8 == BM && NW <= WN, "re-tiling must cover the 128 rows with all consumer warps");
-    const int jb = it.nJ - 1, noff = jb * kKbPerJ, ke = (jb + 1) * kKbPerJ;
+    const int jb = it.nJ - 1, noff = jb * kKbPerJ, ke = it.kmax;   // (kmax <= nJ * 8: the padding slabs are skipped)
     const int row0 = (warp / NW) * MA2 * 8, wn2 = warp % NW, col0 = wn2 * NB2 * 8;
     double acc[MA2][NB2][2];
 #pragma unroll
