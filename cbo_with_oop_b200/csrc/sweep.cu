@@ -21,7 +21,7 @@ constexpr int kSweepThreads = CBO_SWEEP_TILE;
 // Shared-memory image of one set's posterior: L^-1 is NOT formed; the forward substitution reads L rows (packed lower
 // triangle) as warp-wide broadcasts.
 struct SweepSmem {
-    double* Lp;    // packed lower triangle, row i at i(i+1)/2
+    double* Lp;    // packed lower triangle, row i at i(i+1)/2, diagonal entries inverted
     double* al;    // alpha
     double* sv;    // sqrt(v_int)
     double* xs;    // x_int, n x d
@@ -51,7 +51,7 @@ __device__ __forceinline__ void posterior_at(const SweepSmem& sm, int n, int d, 
                 double a = ks;
 #pragma unroll
                 for (int j = 0; j < i; ++j) a = fma(-Li[j], t[j], a);
-                t[i] = a / Li[i];
+                t[i] = a * Li[i];     // Li[i] = 1 / L[i][i]: one division per set entry at staging, not one per candidate and row
                 ss = fma(t[i], t[i], ss);
             }
         }
@@ -67,7 +67,7 @@ __device__ __forceinline__ void posterior_at(const SweepSmem& sm, int n, int d, 
             const double* __restrict__ Li = sm.Lp + i * (i + 1) / 2;
             double a = ks;
             for (int j = 0; j < i; ++j) a = fma(-Li[j], sm.tcol[j * kSweepThreads + tid], a);
-            const double tt = a / Li[i];
+            const double tt = a * Li[i];
             sm.tcol[i * kSweepThreads + tid] = tt;
             ss = fma(tt, tt, ss);
         }
@@ -98,7 +98,7 @@ sweep_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, double best, d
     if (!cached) {
         for (int e = tid; e < n * n; e += kSweepThreads) {
             const int i = e / n, j = e % n;
-            if (j <= i) sm.Lp[i * (i + 1) / 2 + j] = S.L[e];
+            if (j <= i) sm.Lp[i * (i + 1) / 2 + j] = j < i ? S.L[e] : 1.0 / S.L[e];   // the diagonal is staged as its reciprocal
         }
         for (int i = tid; i < n; i += kSweepThreads) {
             sm.al[i] = S.alpha[i];
