@@ -30,6 +30,7 @@
 // SURVEY.md §8(d) is 2 N^2 + 2 N + d N.  Scratch traffic: each U slab is re-read once per J block
 // (~N/256 times), about 1 TB/s of L2/HBM reads chip-wide at N = 1e4 -- 15 % of HBM bandwidth.
 #include "dmma_tile.cuh"
+#include "prior_pair.cuh"
 
 namespace cbo {
 
@@ -41,8 +42,11 @@ constexpr int kPartialFloor = 1024;                    // partial slots every wo
 
 // (this file is the grid / explicit-point evaluation, cbo_prior_eval which == 0; the interventional rows, which == 1,
 // are evaluated in compensated arithmetic by prior_rows.cu)
-__host__ __device__ inline long long prior_tiles(const cbo_set_desc& S) {
-    if (!computes_prior(S)) return 0;
+// split = {chunk, nsplit}: chunk > 0 -> segments; else nsplit > 1 -> folded column blocks; else one item per tile.
+// skip_pair: the launch leaves the sets of the small-N tensor-grid path (prior_pair.cu) alone -- they count no tiles here.
+struct PriorSplit { int chunk, nsplit, skip_pair; };
+__host__ __device__ inline long long prior_tiles(const cbo_set_desc& S, PriorSplit sp) {
+    if (!computes_prior(S) || (sp.skip_pair && pair_eligible(S))) return 0;
     return (S.g_count + CBO_PRIOR_TILE - 1) / CBO_PRIOR_TILE;
 }
 __host__ __device__ inline int prior_nJ(const cbo_set_desc& S) { return (S.n_obs + kMBlkRows - 1) / kMBlkRows; }
@@ -67,13 +71,11 @@ __host__ __device__ inline int prior_nsplit(const cbo_set_desc& S, int nsplit) {
     const int nJ = prior_nJ(S), cap = nJ / 2 > 1 ? nJ / 2 : 1;
     return nsplit < cap ? nsplit : cap;
 }
-// split = {chunk, nsplit}: chunk > 0 -> segments; else nsplit > 1 -> folded column blocks; else one item per tile
-struct PriorSplit { int chunk, nsplit; };
 __host__ __device__ inline long long prior_items_per_tile(const cbo_set_desc& S, PriorSplit sp) {
     return sp.chunk > 0 ? prior_F(prior_nJ(S), sp.chunk) : prior_nsplit(S, sp.nsplit);
 }
 __host__ __device__ inline long long prior_items(const cbo_set_desc& S, PriorSplit sp) {
-    return prior_tiles(S) * prior_items_per_tile(S, sp);
+    return prior_tiles(S, sp) * prior_items_per_tile(S, sp);
 }
 
 template <int WM_, int WN_, int MA_, int NB_, int STAGES_>
@@ -555,7 +557,7 @@ prior_finalize_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, Prior
     long long base = 0;
     for (int s = 0; s < num_sets; ++s) {
         const cbo_set_desc& S = sets[s];
-        const int tiles = (int)prior_tiles(S);
+        const int tiles = (int)prior_tiles(S, split);
         if (tiles == 0) continue;
         const int per = (int)prior_items_per_tile(S, split);
         if (per > 1) {
@@ -597,10 +599,15 @@ size_t prior_rows_workspace_bytes(const cbo_set_desc* h_sets, int num_sets);
 int prior_rows_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_sets, void* d_ws, size_t ws_bytes,
                     size_t ws_offset, cudaStream_t st);
 
-// workspace = [256 B header][partials][ctas scratch slots]; the interventional-rows kernel (which == 1, prior_rows.cu) runs
-// stream-ordered with the grid kernel and reuses everything behind the header for its own partials
+// workspace = [256 B header][pair tables of the small-N tensor-grid sets (prior_pair.cu)][partials][ctas scratch slots];
+// the interventional-rows kernel (which == 1, prior_rows.cu) runs stream-ordered with the grid kernels and reuses
+// everything behind the header for its own partials (the pair tables are rebuilt by every which == 0 call)
+static size_t pair_area_bytes(const cbo_set_desc* h_sets, int num_sets) {
+    return (pair_area_doubles(h_sets, num_sets) * sizeof(double) + 255) / 256 * 256;
+}
+
 size_t prior_workspace_bytes_impl(const cbo_set_desc* h_sets, int num_sets, int num_ctas) {
-    const size_t grid = prior_partial_items(num_ctas) * kPartialDoubles * sizeof(double) +
+    const size_t grid = pair_area_bytes(h_sets, num_sets) + prior_partial_items(num_ctas) * kPartialDoubles * sizeof(double) +
                         (size_t)num_ctas * prior_slot_doubles(h_sets, num_sets) * sizeof(double);
     const size_t rows = prior_rows_workspace_bytes(h_sets, num_sets);
     return kPriorWsHeader + (grid > rows ? grid : rows);
@@ -609,32 +616,44 @@ size_t prior_workspace_bytes_impl(const cbo_set_desc* h_sets, int num_sets, int 
 int prior_eval_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_sets, int which, void* d_ws,
                     size_t ws_bytes, cudaStream_t st) {
     if (which == 1) return prior_rows_impl(h_sets, d_sets, num_sets, d_ws, ws_bytes, kPriorWsHeader, st);
+    int dev = 0, sms = 0;
+    CBO_CUDA(cudaGetDevice(&dev));
+    CBO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const size_t slot = prior_slot_doubles(h_sets, num_sets);
+    const size_t fixed = kPriorWsHeader + (size_t)kPartialFloor * kPartialDoubles * sizeof(double);
+    const size_t per_cta = 4 * kPartialDoubles * sizeof(double) + slot * sizeof(double);
+    // the pair area is part of the layout whenever the workspace has room for it next to one scratch slot (it always has
+    // when it was sized with cbo_prior_workspace_bytes); a smaller workspace runs every set through the general kernel
+    size_t pair_bytes = pair_area_bytes(h_sets, num_sets);
+    if (d_ws == nullptr || ws_bytes < fixed + per_cta + pair_bytes) pair_bytes = 0;
+    // The small-N path needs enough (scale row, tile) items to occupy the GPU: a launch with fewer items than SMs (one or
+    // two small 2-D grids, e.g. the complete graph's six sets) is served better by the general kernel's segment split.
+    PriorSplit split{0, 1, 0};
+    if (pair_bytes > 0 && pair_items_total(h_sets, num_sets) >= sms) split.skip_pair = 1;
+    if (split.skip_pair) {
+        const int rc = prior_pair_impl(h_sets, d_sets, num_sets, reinterpret_cast<double*>(static_cast<unsigned char*>(d_ws) + kPriorWsHeader),
+                                       sms, st);
+        if (rc != 0) return rc;
+    }
     long long tiles = 0;
     for (int s = 0; s < num_sets; ++s) {
         const cbo_set_desc& S = h_sets[s];
-        if (!computes_prior(S)) continue;
+        if (prior_tiles(S, split) == 0) continue;
         for (int k = 0; k < (S.points ? 1 : S.d); ++k) {
             const long long pk = S.points ? S.g_total : (long long)S.p[k];
             CBO_REQUIRE(pk * (long long)S.n_obs_pad < 2147483647LL, "cbo_prior_eval: table %d of set %d too large", k, s);
         }
         CBO_REQUIRE((long long)CBO_PRIOR_TILE * S.n_obs_pad < 2147483647LL, "cbo_prior_eval: set %d n_obs_pad too large", s);
-        tiles += prior_tiles(S);
+        tiles += prior_tiles(S, split);
     }
     if (tiles == 0) return 0;
-    const size_t slot = prior_slot_doubles(h_sets, num_sets);
-    const size_t fixed = kPriorWsHeader + (size_t)kPartialFloor * kPartialDoubles * sizeof(double);
-    const size_t per_cta = 4 * kPartialDoubles * sizeof(double) + slot * sizeof(double);
-    CBO_REQUIRE(d_ws != nullptr && ws_bytes >= fixed + per_cta,
+    CBO_REQUIRE(d_ws != nullptr && ws_bytes >= fixed + per_cta + pair_bytes,
                 "cbo_prior_eval: workspace of %zu bytes cannot hold one scratch slot (%zu bytes needed); see cbo_prior_workspace_bytes",
-                ws_bytes, fixed + per_cta);
-    int dev = 0, sms = 0;
-    CBO_CUDA(cudaGetDevice(&dev));
-    CBO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    long long ctas = (long long)((ws_bytes - fixed) / per_cta);
+                ws_bytes, fixed + per_cta + pair_bytes);
+    long long ctas = (long long)((ws_bytes - fixed - pair_bytes) / per_cta);
     if (ctas > sms) ctas = sms;      // one CTA per SM (shared memory bound); more slots than SMs are not used
     // too few tiles to fill the GPU twice over: cut every tile's triangle of M into segments (as fine as the partial
     // buffer and a 4-items-per-CTA budget allow); when even the coarsest segments do not fit, deal out column blocks
-    PriorSplit split{0, 1};
     auto count = [&](PriorSplit sp) {
         long long t = 0;
         for (int s = 0; s < num_sets; ++s) t += prior_items(h_sets[s], sp);
@@ -643,10 +662,10 @@ int prior_eval_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int 
     if (tiles < 2 * ctas) {
         int nJmax = 1;
         for (int s = 0; s < num_sets; ++s)
-            if (prior_tiles(h_sets[s]) > 0 && prior_nJ(h_sets[s]) > nJmax) nJmax = prior_nJ(h_sets[s]);
+            if (prior_tiles(h_sets[s], split) > 0 && prior_nJ(h_sets[s]) > nJmax) nJmax = prior_nJ(h_sets[s]);
         const long long budget = (long long)prior_partial_items(ctas) < 4 * ctas ? (long long)prior_partial_items(ctas) : 4 * ctas;
         for (int c = 1; c <= nJmax && nJmax > 1; ++c)
-            if (count(PriorSplit{c, 1}) <= budget) { split.chunk = c; break; }
+            if (count(PriorSplit{c, 1, split.skip_pair}) <= budget) { split.chunk = c; break; }
         if (split.chunk == 0) {
             split.nsplit = (int)((2 * ctas + tiles - 1) / tiles);
             while (split.nsplit > 1 && count(split) > (long long)prior_partial_items(ctas)) --split.nsplit;
@@ -658,7 +677,7 @@ int prior_eval_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int 
     CBO_REQUIRE(!partial || (size_t)total <= prior_partial_items(ctas), "cbo_prior_eval: internal: partial buffer too small");
     const long long grid = ctas < total ? ctas : total;
     unsigned char* ws = reinterpret_cast<unsigned char*>(d_ws);
-    double* partials = reinterpret_cast<double*>(ws + kPriorWsHeader);
+    double* partials = reinterpret_cast<double*>(ws + kPriorWsHeader + pair_bytes);
     double* scratch = partials + prior_partial_items(ctas) * kPartialDoubles;
     auto kern = split.chunk > 0 ? prior_eval_kernel<PriorCfgA, true> : prior_eval_kernel<PriorCfgA, false>;
     CBO_CUDA(allow_dynamic_smem(prior_eval_kernel<PriorCfgA, true>, PriorCfgA::SMEM));

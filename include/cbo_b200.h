@@ -30,7 +30,7 @@ extern "C" {
 #define CBO_API
 #endif
 
-#define CBO_ABI_VERSION 5
+#define CBO_ABI_VERSION 6
 #define CBO_MAX_D 4          /* intervened dimensions per exploration set (reference uses 1..3) */
 #define CBO_MAX_C 8          /* conditioning dimensions of an observational GP */
 #define CBO_MAX_NINT 128     /* interventional rows per set (reference: 10 .. ~50) */
@@ -169,6 +169,11 @@ CBO_API int cbo_prior_precompute(const cbo_set_desc* h_sets, int num_sets, void*
  *            persistent kernel, one CTA per SM; each CTA materialises the 128 x n_obs_pad table product of its current
  *            128 candidates in a private slot of `d_workspace`.  Launches with too few 128-candidate tiles to fill the
  *            GPU cut every tile's triangle of M into segments (deterministic partial sums).
+ *            Small observational sets on 2-D / 3-D tensor grids (n_obs <= 256: the reference's shipped data, 100..200
+ *            rows) take a different decomposition when the call holds at least one work item per SM: u^T M u is
+ *            regrouped over the n_obs (n_obs + 1) / 2 index pairs of the symmetric M, so that a whole plane of the
+ *            grid is one GEMM between two small per-dimension "pair tables" kept in `d_workspace`
+ *            (csrc/prior_pair.cu); cbo_prior_pair_items tells which decomposition a call will use.
  * which = 1: on the interventional rows x_int[int_row_begin .. n_int) (writes m_int, v_int).  These values are the
  *            inputs of the per-set fit, which amplifies their error by the Gram's condition number, so they are
  *            accumulated in compensated (double-double) arithmetic; one pass over M, HBM-bound for a single appended row.
@@ -178,6 +183,10 @@ CBO_API int cbo_prior_precompute(const cbo_set_desc* h_sets, int num_sets, void*
 CBO_API size_t cbo_prior_workspace_bytes(const cbo_set_desc* h_sets, int num_sets, int num_ctas);
 CBO_API int cbo_prior_eval(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_sets, int which,
                            void* d_workspace, size_t workspace_bytes, void* stream);
+/* Host-side arithmetic only: the number of (scale row, tile) work items the pair-table decomposition of
+ * cbo_prior_eval(which = 0) would run for this descriptor list on a device with `num_sms` SMs and a workspace sized
+ * by cbo_prior_workspace_bytes; 0 when every set goes through the general kernel. */
+CBO_API long cbo_prior_pair_items(const cbo_set_desc* h_sets, int num_sets, int num_sms);
 
 /* K2. one CTA per set: Gram of the interventional rows (CausalRBF.K, causal_kernels.py:45-62, or RBF),
  * + (1e-10 + 1e-8) I, Cholesky with GPy's jitter-retry rule, alpha = Ky^-1 (y - m).

@@ -62,7 +62,9 @@ def test_argument_validation_reports_through_last_error(lib):
     assert b"g_total" in lib.cbo_last_error()
     assert lib.cbo_sweep_num_items(h, 1) == 1
     h[0].g_total, h[0].n_obs_pad = 10, 128
-    assert lib.cbo_prior_workspace_bytes(h, 1, 148) == 256 + (4 * 148 + 1024) * 2 * 128 * 8 + 148 * 128 * 128 * 8
+    # header + the (empty) pair-table area's 16 ones, rounded to 256 B + partials + one scratch slot per CTA
+    assert lib.cbo_prior_workspace_bytes(h, 1, 148) == 256 + 256 + (4 * 148 + 1024) * 2 * 128 * 8 + 148 * 128 * 128 * 8
+    assert lib.cbo_prior_pair_items(h, 1, 148) == 0
     with pytest.raises(_lib.CboError):
         _lib.check(-1, "demo")
 
