@@ -52,6 +52,7 @@ class SweepResult(C.Structure):
 EXPORTS = [
     "cbo_abi_version", "cbo_sizeof_set_desc", "cbo_offsetof_set_desc", "cbo_last_error", "cbo_sweep_num_items",
     "cbo_prior_workspace_bytes", "cbo_launch_count", "cbo_obs_gp_workspace_bytes", "cbo_prior_pair_items",
+    "cbo_prior_eval_flops",
     "cbo_obs_gp_fit", "cbo_obs_gp_nll",
     "cbo_build_tables", "cbo_prior_precompute", "cbo_prior_eval", "cbo_posterior_fit", "cbo_sweep",
     "cbo_argmax_combine",
@@ -90,6 +91,8 @@ def load() -> C.CDLL:
     lib.cbo_prior_precompute.argtypes = [P, C.c_int, C.c_void_p]
     lib.cbo_prior_workspace_bytes.restype = C.c_size_t
     lib.cbo_prior_workspace_bytes.argtypes = [P, C.c_int, C.c_int]
+    lib.cbo_prior_eval_flops.restype = C.c_double
+    lib.cbo_prior_eval_flops.argtypes = [P, C.c_int, C.c_int]
     lib.cbo_prior_pair_items.restype = C.c_long
     lib.cbo_prior_pair_items.argtypes = [P, C.c_int, C.c_int]
     lib.cbo_obs_gp_workspace_bytes.restype = C.c_size_t
@@ -101,7 +104,7 @@ def load() -> C.CDLL:
     lib.cbo_sweep.argtypes = [P, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_void_p]
     lib.cbo_argmax_combine.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
-    for name in EXPORTS[9:]:
+    for name in EXPORTS[10:]:
         getattr(lib, name).restype = C.c_int
     if lib.cbo_abi_version() != CBO_ABI_VERSION:
         raise ImportError(f"ABI version mismatch: library {lib.cbo_abi_version()} != binding {CBO_ABI_VERSION}")

@@ -62,6 +62,7 @@ int prior_precompute_impl(const cbo_set_desc*, int, cudaStream_t);
 int prior_eval_impl(const cbo_set_desc*, const cbo_set_desc*, int, int, void*, size_t, cudaStream_t);
 size_t prior_workspace_bytes_impl(const cbo_set_desc*, int, int);
 long long pair_items_total(const cbo_set_desc*, int);
+double prior_eval_flops_impl(const cbo_set_desc*, int, int);
 int posterior_fit_impl(const cbo_set_desc*, const cbo_set_desc*, int, cudaStream_t);
 int sweep_impl(const cbo_set_desc*, const cbo_set_desc*, int, double, int, cbo_set_best*, cbo_set_best*, cbo_sweep_result*,
                cudaStream_t);
@@ -135,6 +136,11 @@ long cbo_prior_pair_items(const cbo_set_desc* h_sets, int num_sets, int num_sms)
     if (!h_sets || num_sets < 1 || num_sms < 1) return 0;
     const long long t = pair_items_total(h_sets, num_sets);
     return t >= num_sms ? (long)t : 0;
+}
+
+double cbo_prior_eval_flops(const cbo_set_desc* h_sets, int num_sets, int num_sms) {
+    if (!h_sets || num_sets < 1 || num_sms < 1) return 0.0;
+    return prior_eval_flops_impl(h_sets, num_sets, num_sms);
 }
 
 int cbo_prior_eval(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_sets, int which, void* d_workspace,

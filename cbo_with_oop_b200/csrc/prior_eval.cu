@@ -613,6 +613,33 @@ size_t prior_workspace_bytes_impl(const cbo_set_desc* h_sets, int num_sets, int 
     return kPriorWsHeader + (grid > rows ? grid : rows);
 }
 
+// FP64 flops issued through DMMA by one which == 0 call (cbo_prior_eval_flops): the pair-table sets when the call takes
+// that path (at least one item per SM), everything else through the general kernel's lower block triangle.
+double prior_eval_flops_impl(const cbo_set_desc* h_sets, int num_sets, int num_sms) {
+    const bool pair = pair_items_total(h_sets, num_sets) >= num_sms;
+    double fl = 0.0;
+    for (int s = 0; s < num_sets; ++s) {
+        const cbo_set_desc& S = h_sets[s];
+        if (!computes_prior(S) || S.g_count == 0) continue;
+        if (pair && pair_eligible(S)) {
+            const PairGeom g = pair_geom(S);
+            double blocks = 0.0;    // live 8 x 8 blocks of all tiles of one plane
+            for (int ca = 0; ca < g.nchA; ++ca)
+                for (int cb = 0; cb < g.nchB; ++cb) {
+                    const int ra = g.pa - ca * g.CRa, rb = g.pb - cb * g.CRb;
+                    blocks += (double)(((ra < g.CRa ? ra : g.CRa) + 7) / 8) * (((rb < g.CRb ? rb : g.CRb) + 7) / 8);
+                }
+            fl += 2.0 * 64.0 * blocks * g.s_count * (double)g.Kslabs * kBK;
+        } else {
+            const int nJ = prior_nJ(S), lc = S.n_obs - (nJ - 1) * kMBlkRows;
+            const int last_cols = (nJ == 1 || lc > 64) ? 128 : (lc <= 16 ? 16 : (lc <= 32 ? 32 : 64));
+            const double n16 = (double)((S.n_obs + kBK - 1) / kBK * kBK);
+            fl += (double)S.g_count * 2.0 * (128.0 * 128.0 * (nJ - 1) * nJ / 2.0 + last_cols * n16);
+        }
+    }
+    return fl;
+}
+
 int prior_eval_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_sets, int which, void* d_ws,
                     size_t ws_bytes, cudaStream_t st) {
     if (which == 1) return prior_rows_impl(h_sets, d_sets, num_sets, d_ws, ws_bytes, kPriorWsHeader, st);

@@ -455,8 +455,9 @@ class SweepEngine:
             from .dist import gather_set_bests
             gather_set_bests(gb, self.gathered, self.world, self.group)
             src, nr = self.gathered, self.world
-        else:
-            src, nr = gb, 1
+        else:   # combine_kernel's input and output must not alias (both are __restrict__): stage the table like a 1-rank gather
+            self.gathered[:gb.numel()].copy_(gb)
+            src, nr = self.gathered, 1
         _lib.check(self.lib.cbo_argmax_combine(C.c_void_p(src.data_ptr()), nr, S, C.c_void_p(gb.data_ptr()),
                                                C.c_void_p(self.result.data_ptr()), self._stream()), "cbo_argmax_combine")
         out_h = self.out_buf.cpu().numpy().tobytes()     # ONE device -> host read of the step's result (synchronises)

@@ -30,8 +30,18 @@ def fit_state(X: np.ndarray, y: np.ndarray, s2: float, ls, noise: float = 1e-2, 
     if ls is None:
         raise ValueError("lengthscale must have 1 or D entries")
     if device is None:
+        # host path: input preparation for fixtures / small shipped graphs (the agent fits on the device, CBO.observe).
+        # Same jitter ladder as the device path and GPy's jitchol: mean(diag) * 1e-6 * 10^t, t = 0..4.
         Ky = rbf_gram(X, s2, ls) + (noise + GPY_JITTER) * np.eye(N)
-        L = np.linalg.cholesky(Ky)
+        jitter, L = 0.0, None
+        for t in range(6):
+            try:
+                L = np.linalg.cholesky(Ky + jitter * np.eye(N) if jitter else Ky)
+                break
+            except np.linalg.LinAlgError:
+                if t == 5 or np.any(np.diag(Ky) <= 0.0):
+                    raise np.linalg.LinAlgError("observational Gram matrix not positive definite, even with jitter")
+                jitter = float(np.mean(np.diag(Ky))) * 1e-6 if t == 0 else jitter * 10.0
         kyinv = scipy.linalg.cho_solve((L, True), np.eye(N))
         kyinv = 0.5 * (kyinv + kyinv.T)
         return kyinv @ y, kyinv

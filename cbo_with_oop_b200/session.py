@@ -50,8 +50,10 @@ class AcquisitionSession:
         pr = self.engine.problems[g]
         x_int = np.asarray(x_int, np.float64).reshape(-1, pr.d)
         y_int = np.asarray(y_int, np.float64).reshape(-1)
-        if x_int.shape == pr.x_int.shape and np.array_equal(x_int, pr.x_int) and np.array_equal(y_int, pr.y_int) \
-                and g not in self.stale_fit:
+        # unchanged data: nothing to do, whether or not the set is already waiting for a refit (Monitor.add_intervention_data
+        # -> model.set_data marks the set first; the next compute_best_acquisition_values then passes the same arrays again
+        # and must not reset the appended-row bookkeeping of the engine)
+        if x_int.shape == pr.x_int.shape and np.array_equal(x_int, pr.x_int) and np.array_equal(y_int, pr.y_int):
             return
         self.engine.set_interventional(g, x_int, y_int)
         self.stale_fit.add(g)

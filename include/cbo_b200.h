@@ -187,6 +187,11 @@ CBO_API int cbo_prior_eval(const cbo_set_desc* h_sets, const cbo_set_desc* d_set
  * cbo_prior_eval(which = 0) would run for this descriptor list on a device with `num_sms` SMs and a workspace sized
  * by cbo_prior_workspace_bytes; 0 when every set goes through the general kernel. */
 CBO_API long cbo_prior_pair_items(const cbo_set_desc* h_sets, int num_sets, int num_sms);
+/* Host-side arithmetic only: FP64 flops (2 per multiply-add) that the DMMA instructions of ONE cbo_prior_eval(which = 0)
+ * call issue for this descriptor list -- the numerator of the kernel's FP64-pipe utilisation (bench.py's roofline).
+ * General kernel: per candidate, the lower block triangle of M in 128 x 128 blocks (ragged last column block re-tiled);
+ * pair-table kernel: per work item, (live 8 x 8 blocks of the tile) x (pair + mean columns, padded to 16). */
+CBO_API double cbo_prior_eval_flops(const cbo_set_desc* h_sets, int num_sets, int num_sms);
 
 /* K2. one CTA per set: Gram of the interventional rows (CausalRBF.K, causal_kernels.py:45-62, or RBF),
  * + (1e-10 + 1e-8) I, Cholesky with GPy's jitter-retry rule, alpha = Ky^-1 (y - m).

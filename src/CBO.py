@@ -41,6 +41,9 @@ class CBO:
         self.grid_points_per_dim = getattr(args, "grid_points", 100)
         self.device = getattr(args, "device", "cuda:0")
         self.num_sem_samples = getattr(args, "num_sem_samples", 100000)
+        # where observe() fits the observational GPs: "device" (cbo_obs_gp_fit / cbo_obs_gp_nll, the default) or, on explicit
+        # request only, "host" (SciPy; input preparation for machines without a GPU -- the sweep itself has no CPU path)
+        self.observational_fit = getattr(args, "observational_fit", "device")
 
         self.mean_functions, self.var_functions, self.models = [], [], []
         self.costs = self.graph.get_cost_structure(type_cost=self.type_cost)
@@ -87,7 +90,8 @@ class CBO:
         self.monitor.log_agent_behaviour(act=False)
         self.measurements = pd.concat([self.measurements, self.get_new_observation()])
         if self.gp_type == GPType.CAUSAL_GP:
-            gaussian_processes = self.graph.fit_all_gaussian_processes(self.measurements)
+            fit_device = self.device if self.observational_fit == "device" else None
+            gaussian_processes = self.graph.fit_all_gaussian_processes(self.measurements, device=fit_device)
             self.mean_functions, self.var_functions = self.do_calculus.update_all_do_functions(gaussian_processes)
         else:
             self.mean_functions, self.var_functions = [None] * self.es_size, [None] * self.es_size

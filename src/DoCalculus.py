@@ -90,7 +90,12 @@ class DoCalculus:
             else np.asarray(gp.lengthscale, np.float64)
         fix, variable = cbo.graph.fixed_cost_of(variables, cbo.type_cost)
         mon = cbo.monitor
-        return SetProblem(x_obs_int=gp.X[:, pos], x_obs_cond=gp.X[:, rest], mc_cond=gp.X[:, rest], alpha_obs=gp.alpha, kyinv=gp.kyinv,
+        # a GP fitted by the agent carries no host-side Ky^-1: the engine forms alpha and Ky^-1 in HBM from (X, y)
+        # (cbo_obs_gp_fit), so no N x N array crosses PCIe
+        on_device = getattr(gp, "device_fit", False)
+        state = dict(alpha_obs=None, kyinv=None, y_obs=np.asarray(gp.Y, np.float64).reshape(-1)) if on_device else \
+            dict(alpha_obs=gp.alpha, kyinv=gp.kyinv)
+        return SetProblem(x_obs_int=gp.X[:, pos], x_obs_cond=gp.X[:, rest], mc_cond=gp.X[:, rest], **state,
                           ls_int=ls[pos], ls_cond=ls[rest], s2=gp.variance, noise=gp.noise,
                           grid=mon.space_list[s].grid_tables(cbo.grid_points_per_dim), x_int=mon.data_x[s],
                           y_int=mon.data_y[s].reshape(-1), cost_fix=fix, cost_variable=variable, causal=True, name="".join(variables))

@@ -81,9 +81,10 @@ class GraphInterface(abc.ABC):
         return self.get_gp_name(self.prior_columns(intervention_set))
 
     # ---- observational GPs ----------------------------------------------------------------------------
-    def fit_all_gaussian_processes(self, measurements=None):
+    def fit_all_gaussian_processes(self, measurements=None, device=None):
         """One observational GP (RBF, noise fixed to 1e-2, hyper-parameters optimised; reference utils.py:40-45)
-        per exploration set of MIS, keyed by its gp name.  `measurements` may be a DataFrame or a dict of columns."""
+        per exploration set of MIS, keyed by its gp name.  `measurements` may be a DataFrame or a dict of columns.
+        `device` (the agent passes cbo.device): fit on the GPU -- see utils.fit_gaussian_process."""
         from src.utils_functions.utils import fit_gaussian_process
         data = self.measurements if measurements is None else {
             name: np.asarray(measurements[name], np.float64).reshape(-1, 1) for name in self.var_names}
@@ -94,7 +95,7 @@ class GraphInterface(abc.ABC):
             if name in gps:
                 continue
             x = np.hstack([data[c] for c in cols])
-            gps[name] = fit_gaussian_process(x, data["Y"], self.fit_parameters_for(cols))
+            gps[name] = fit_gaussian_process(x, data["Y"], self.fit_parameters_for(cols), device=device)
             gps[name].columns = cols
         return gps
 

@@ -12,7 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def make_args(**kw):
     base = dict(exploration_set="MIS", initial_num_obs_samples=100, num_interventions=10, type_cost=1,
                 num_additional_observations=20, num_trials=4, name_index=0, seed=9, causal_prior=True, experiment="complete_graph",
-                task="min", grid_points=20, device="cuda:0", num_sem_samples=500)
+                task="min", grid_points=20, device="cuda:0", num_sem_samples=500,
+                observational_fit="host")
     base.update(kw)
     return types.SimpleNamespace(**base)
 
