@@ -15,7 +15,7 @@ CBO_MAX_NINT = 128
 CBO_NPAD = 128
 CBO_SPAD = 16
 CBO_PRIOR_TILE = 128
-CBO_SWEEP_TILE = 128
+CBO_SWEEP_TILE = 1024
 
 _dp = C.c_void_p  # device pointer
 
@@ -87,8 +87,8 @@ def load() -> C.CDLL:
     P = C.POINTER(SetDesc)
     lib.cbo_sweep_num_items.restype = C.c_long
     lib.cbo_sweep_num_items.argtypes = [P, C.c_int]
-    lib.cbo_build_tables.argtypes = [P, C.c_int, C.c_void_p]
-    lib.cbo_prior_precompute.argtypes = [P, C.c_int, C.c_void_p]
+    lib.cbo_build_tables.argtypes = [P, C.c_void_p, C.c_int, C.c_void_p]
+    lib.cbo_prior_precompute.argtypes = [P, C.c_void_p, C.c_int, C.c_void_p]
     lib.cbo_prior_workspace_bytes.restype = C.c_size_t
     lib.cbo_prior_workspace_bytes.argtypes = [P, C.c_int, C.c_int]
     lib.cbo_prior_eval_flops.restype = C.c_double

@@ -57,8 +57,8 @@ int validate_sets(const cbo_set_desc* h_sets, int num_sets) {
     return 0;
 }
 
-int build_tables_impl(const cbo_set_desc*, int, cudaStream_t);
-int prior_precompute_impl(const cbo_set_desc*, int, cudaStream_t);
+int build_tables_impl(const cbo_set_desc*, const cbo_set_desc*, int, cudaStream_t);
+int prior_precompute_impl(const cbo_set_desc*, const cbo_set_desc*, int, cudaStream_t);
 int prior_eval_impl(const cbo_set_desc*, const cbo_set_desc*, int, int, void*, size_t, cudaStream_t);
 size_t prior_workspace_bytes_impl(const cbo_set_desc*, int, int);
 long long pair_items_total(const cbo_set_desc*, int);
@@ -117,14 +117,14 @@ int cbo_obs_gp_nll(const cbo_set_desc* h_set, void* d_workspace, size_t workspac
     return obs_gp_nll_impl(h_set, d_workspace, workspace_bytes, d_out, (cudaStream_t)stream);
 }
 
-int cbo_build_tables(const cbo_set_desc* h_sets, int num_sets, void* stream) {
+int cbo_build_tables(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_sets, void* stream) {
     if (int rc = validate_sets(h_sets, num_sets)) return rc;
-    return build_tables_impl(h_sets, num_sets, (cudaStream_t)stream);
+    return build_tables_impl(h_sets, d_sets, num_sets, (cudaStream_t)stream);
 }
 
-int cbo_prior_precompute(const cbo_set_desc* h_sets, int num_sets, void* stream) {
+int cbo_prior_precompute(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_sets, void* stream) {
     if (int rc = validate_sets(h_sets, num_sets)) return rc;
-    return prior_precompute_impl(h_sets, num_sets, (cudaStream_t)stream);
+    return prior_precompute_impl(h_sets, d_sets, num_sets, (cudaStream_t)stream);
 }
 
 size_t cbo_prior_workspace_bytes(const cbo_set_desc* h_sets, int num_sets, int num_ctas) {

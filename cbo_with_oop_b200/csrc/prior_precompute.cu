@@ -122,22 +122,158 @@ syrk_kernel(const double* __restrict__ P, int n_mc_pad, const double* __restrict
     }
 }
 
-int prior_precompute_impl(const cbo_set_desc* h_sets, int num_sets, cudaStream_t st) {
+// ---- batched forms: every set of the call in ONE launch per stage (the reference's shipped sizes are 25 sets of
+// N = 100..200 -- per-set launches cost more than the work).  Needs the descriptors on the device and a private P
+// buffer per set; prior_precompute_impl falls back to per-set launches otherwise.
+__global__ void __launch_bounds__(256)
+pgen_batched_kernel(const cbo_set_desc* __restrict__ sets) {
+    __shared__ double red[8];
+    const cbo_set_desc& S = sets[blockIdx.y];
+    if (!computes_prior(S) || S.c == 0) return;
+    const int c = S.c, n_obs = S.n_obs, n_mc = S.n_mc, n_mc_pad = S.n_mc_pad;
+    double il[CBO_MAX_C];
+#pragma unroll
+    for (int k = 0; k < CBO_MAX_C; ++k) il[k] = k < c ? 1.0 / S.ls_cond[k] : 0.0;
+    for (int j = blockIdx.x; j < S.n_obs_pad; j += gridDim.x) {
+        double* __restrict__ row = S.P + (size_t)j * n_mc_pad;
+        const bool live = j < n_obs;
+        double xj[CBO_MAX_C];
+#pragma unroll
+        for (int k = 0; k < CBO_MAX_C; ++k) xj[k] = (live && k < c) ? S.x_obs_cond[(size_t)k * n_obs + j] : 0.0;
+        double sum = 0.0;
+        for (int i = threadIdx.x; i < n_mc_pad; i += 256) {
+            double val = 0.0;
+            if (live && i < n_mc) {
+                double r2 = 0.0;
+#pragma unroll
+                for (int k = 0; k < CBO_MAX_C; ++k) {
+                    if (k < c) {
+                        const double t = (S.mc_cond[(size_t)k * n_mc + i] - xj[k]) * il[k];
+                        r2 += t * t;
+                    }
+                }
+                val = exp(-0.5 * r2);
+            }
+            row[i] = val;
+            sum += val;
+        }
+        sum = warp_sum(sum);
+        __syncthreads();                       // red[] of the previous row has been read
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+#pragma unroll
+            for (int x = 0; x < 8; ++x) t += red[x];
+            const double pb = live ? t / (double)n_mc : 0.0;
+            S.pbar[j] = pb;
+            S.w[j] = live ? S.s2 * S.alpha_obs[j] * pb : 0.0;
+        }
+    }
+}
+
+template <int WM, int WN, int MA, int NB, int STAGES>
+__global__ void __launch_bounds__(WM * WN * 32, 1)
+syrk_batched_kernel(const cbo_set_desc* __restrict__ sets, int num_sets) {
+    constexpr int BM = WM * MA * 8, BN = WN * NB * 8;
+    constexpr int TILE = BM * kBK;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* sA = reinterpret_cast<double*>(smem_raw);
+    double* sB = sA + STAGES * TILE;
+    // (set, lower-triangle tile) of this CTA: sets with conditioning columns only, tiles in set order
+    int s = 0, t = blockIdx.x;
+    for (; s < num_sets; ++s) {
+        if (!computes_prior(sets[s]) || sets[s].c == 0) continue;
+        const int nT = sets[s].n_obs_pad / CBO_NPAD, cnt = nT * (nT + 1) / 2;
+        if (t < cnt) break;
+        t -= cnt;
+    }
+    if (s >= num_sets) return;
+    const cbo_set_desc& S = sets[s];
+    const double* __restrict__ P = S.P;
+    const double* __restrict__ kyinv = S.kyinv;
+    double* __restrict__ M = S.M;
+    const int n_mc_pad = S.n_mc_pad, n_obs = S.n_obs, n_obs_pad = S.n_obs_pad;
+    const double coef = (S.s2 * S.s2) / (double)S.n_mc;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp / WN, wn = warp % WN;
+    const int row0 = wm * MA * 8, col0 = wn * NB * 8;
+    int bi, bj;
+    tri_tile(t, bi, bj);
+    double acc[MA][NB][2];
+#pragma unroll
+    for (int mi = 0; mi < MA; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NB; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    abt_mainloop<WM, WN, MA, NB, STAGES>(P + (size_t)bi * BM * n_mc_pad, n_mc_pad, P + (size_t)bj * BN * n_mc_pad, n_mc_pad,
+                                         n_mc_pad / kBK, sA, sB, acc, tid);
+#pragma unroll
+    for (int mi = 0; mi < MA; ++mi) {
+        const int r = bi * BM + row0 + mi * 8 + (lane >> 2);
+#pragma unroll
+        for (int ni = 0; ni < NB; ++ni) {
+            const int cidx = bj * BN + col0 + ni * 8 + (lane & 3) * 2;
+            double v0 = 0.0, v1 = 0.0;
+            if (r < n_obs) {
+                if (cidx < n_obs) v0 = coef * kyinv[(size_t)r * n_obs + cidx] * acc[mi][ni][0];
+                if (cidx + 1 < n_obs) v1 = coef * kyinv[(size_t)r * n_obs + cidx + 1] * acc[mi][ni][1];
+            }
+            *reinterpret_cast<double2*>(M + mblk_off(r, cidx, n_obs_pad)) = make_double2(v0, v1);
+            if (bi != bj) {
+                M[mblk_off(cidx, r, n_obs_pad)] = v0;
+                M[mblk_off(cidx + 1, r, n_obs_pad)] = v1;
+            }
+        }
+    }
+}
+
+int prior_precompute_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_sets, cudaStream_t st) {
     constexpr int STAGES = 4;
     constexpr size_t SMEM = (size_t)STAGES * 2 * CBO_NPAD * kBK * sizeof(double);
     auto kern = syrk_kernel<2, 4, 8, 4, STAGES>;
     CBO_CUDA(allow_dynamic_smem(kern, SMEM));
+    // batched launches need the descriptors on the device and P buffers that no two sets share
+    bool batched = d_sets != nullptr && num_sets > 1;
+    long long tiles_total = 0;
+    int npad_max = 0;
     for (int s = 0; s < num_sets; ++s) {
         const cbo_set_desc& S = h_sets[s];
         if (!computes_prior(S)) continue;
         CBO_REQUIRE(S.kyinv && S.alpha_obs && S.M && S.w && S.pbar, "cbo_prior_precompute: set %d has a NULL pointer", s);
+        if (S.c == 0) continue;
+        CBO_REQUIRE(S.P && S.x_obs_cond && S.mc_cond, "cbo_prior_precompute: set %d has a NULL P/x_obs_cond/mc_cond", s);
+        const int nT = S.n_obs_pad / CBO_NPAD;
+        tiles_total += (long long)nT * (nT + 1) / 2;
+        if (S.n_obs_pad > npad_max) npad_max = S.n_obs_pad;
+        const double* e0 = S.P + (size_t)S.n_obs_pad * S.n_mc_pad;
+        for (int t = 0; t < s && batched; ++t) {
+            const cbo_set_desc& T = h_sets[t];
+            if (!computes_prior(T) || T.c == 0) continue;
+            const double* e1 = T.P + (size_t)T.n_obs_pad * T.n_mc_pad;
+            if (S.P < e1 && T.P < e0) batched = false;     // overlapping scratch: the sets must run one after the other
+        }
+    }
+    if (batched && tiles_total > 0 && tiles_total < 2147483647LL) {
+        pgen_batched_kernel<<<dim3((unsigned)(npad_max < 1024 ? npad_max : 1024), (unsigned)num_sets), 256, 0, st>>>(d_sets);
+        note_launch();
+        CBO_CUDA(cudaGetLastError());
+        auto bk = syrk_batched_kernel<2, 4, 8, 4, STAGES>;
+        CBO_CUDA(allow_dynamic_smem(bk, SMEM));
+        bk<<<(unsigned)tiles_total, 256, SMEM, st>>>(d_sets, num_sets);
+        note_launch();
+        CBO_CUDA(cudaGetLastError());
+    }
+    for (int s = 0; s < num_sets; ++s) {
+        const cbo_set_desc& S = h_sets[s];
+        if (!computes_prior(S)) continue;
         if (S.c == 0) {
             nocond_kernel<<<dim3(8, S.n_obs_pad), 256, 0, st>>>(S.kyinv, S.alpha_obs, S.n_obs, S.n_obs_pad, S.s2, S.M, S.pbar, S.w);
             note_launch();
             CBO_CUDA(cudaGetLastError());
             continue;
         }
-        CBO_REQUIRE(S.P && S.x_obs_cond && S.mc_cond, "cbo_prior_precompute: set %d has a NULL P/x_obs_cond/mc_cond", s);
+        if (batched) continue;
         CondParams cp;
         for (int k = 0; k < CBO_MAX_C; ++k) cp.il[k] = k < S.c ? 1.0 / S.ls_cond[k] : 0.0;
         pgen_kernel<<<S.n_obs_pad, 256, 0, st>>>(S.x_obs_cond, S.mc_cond, S.c, S.n_obs, S.n_mc, S.n_mc_pad, cp, S.alpha_obs,

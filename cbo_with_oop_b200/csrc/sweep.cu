@@ -16,7 +16,7 @@
 
 namespace cbo {
 
-constexpr int kSweepThreads = CBO_SWEEP_TILE;
+constexpr int kSweepThreads = 128;     // a work item is CBO_SWEEP_TILE consecutive candidates, kSweepThreads at a time
 
 // Shared-memory image of one set's posterior: L^-1 is NOT formed; the forward substitution reads L rows (packed lower
 // triangle) as warp-wide broadcasts.
@@ -74,7 +74,43 @@ __device__ __forceinline__ void posterior_at(const SweepSmem& sm, int n, int d, 
     }
 }
 
-__global__ void __launch_bounds__(kSweepThreads)
+// Separable form of k* on a tensor grid: exp(-.5 |x - X_I,i|^2) = E_lead[row][i] * E_last[j][i], the product of the
+// leading dimensions' factor (constant along a run of the fastest grid dimension) and the fastest dimension's factor.
+// A work item of CBO_SWEEP_TILE consecutive candidates touches at most CBO_SWEEP_TILE / p_last + 2 leading rows and
+// p_last values of the fastest index, so the CTA evaluates (rows + p_last) * n exponentials once, in shared memory,
+// instead of n per candidate (9x fewer at p = 100, n = 10).  Used when n <= 48 and p_last <= kSepMaxP; otherwise
+// every candidate evaluates its own exponentials (explicit points, very long last dimensions, n > 48).
+constexpr int kSepMaxP = 256;
+__host__ __device__ inline bool sweep_separable(const cbo_set_desc& S) {
+    return !S.points && S.n_int <= 48 && S.p[S.d - 1] <= kSepMaxP && S.p[S.d - 1] >= 16;   // (>= 16: at most 66 leading rows per item)
+}
+__host__ __device__ inline int sweep_lead_rows(const cbo_set_desc& S) { return CBO_SWEEP_TILE / S.p[S.d - 1] + 2; }
+
+template <int NREG>
+__device__ __forceinline__ void posterior_sep(const SweepSmem& sm, int n, const double* __restrict__ eLast, int ldl,
+                                              const double* __restrict__ eLead, int ldr, double svg, double& mu, double& ss) {
+    mu = 0.0; ss = 0.0;
+    double t[NREG];
+#pragma unroll
+    for (int i = 0; i < NREG; ++i) {
+        if (i < n) {
+            const double ks = fma(eLead[i * ldr], eLast[i * ldl], sm.sv[i] * svg);
+            mu = fma(ks, sm.al[i], mu);
+            const double* __restrict__ Li = sm.Lp + i * (i + 1) / 2;
+            double a = ks;
+#pragma unroll
+            for (int j = 0; j < i; ++j) a = fma(-Li[j], t[j], a);
+            t[i] = a * Li[i];
+            ss = fma(t[i], t[i], ss);
+        }
+    }
+}
+
+// NREG: register budget of the forward substitution, picked per LAUNCH from the largest n_int of the call (16 / 32 / 48
+// solution entries in registers; 0: any n, the vector lives in shared memory).  One instantiation per launch keeps the
+// small-n kernel (the reference's n = 10 .. ~50) at a register count that lets many CTAs share an SM.
+template <int NREG>
+__global__ void __launch_bounds__(kSweepThreads, NREG == 16 ? 5 : (NREG == 32 ? 3 : (NREG == 0 ? 5 : 2)))
 sweep_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, double best, double task_sign,
              cbo_set_best* __restrict__ tile_best) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -84,16 +120,27 @@ sweep_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, double best, d
     const int n = S.n_int, d = S.d, tid = threadIdx.x;
     const bool causal = S.causal != 0;
     const bool cached = S.posterior_cached != 0;   // mu / var of an earlier sweep are still valid: EI refresh only
+    const bool sep = NREG > 0 && !cached && sweep_separable(S);
+    const int p_last = S.points ? 1 : S.p[d - 1];
 
     SweepSmem sm;
     sm.Lp = reinterpret_cast<double*>(smem_raw);
     sm.al = sm.Lp + (size_t)n * (n + 1) / 2;
     sm.sv = sm.al + n;
     sm.xs = sm.sv + n;
-    sm.tcol = sm.xs + (size_t)n * CBO_MAX_D;
+    sm.tcol = sm.xs + (size_t)n * CBO_MAX_D;      // generic path (n > 48): [n][threads]; separable path: the two tables
+    const int ldl = p_last | 1, ldr = sweep_lead_rows(S) | 1;          // odd pitches: no bank conflicts
+    double* eLast = sm.tcol;                       // [n][ldl]
+    double* eLead = eLast + (size_t)n * ldl;       // [n][ldr]
     __shared__ double red_v[kSweepThreads / 32];
     __shared__ long long red_i[kSweepThreads / 32];
     __shared__ int red_n[kSweepThreads / 32];
+
+    const long long loc0 = (long long)tile * CBO_SWEEP_TILE;
+    const long long left = S.g_count - loc0;
+    const int cnt = left < CBO_SWEEP_TILE ? (int)left : CBO_SWEEP_TILE;
+    const long long gidx0 = S.g_begin + loc0;
+    const long long row_first = S.points ? gidx0 : gidx0 / p_last;   // first leading row of the item
 
     if (!cached) {
         for (int e = tid; e < n * n; e += kSweepThreads) {
@@ -105,46 +152,60 @@ sweep_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, double best, d
             sm.sv[i] = causal ? S.sqrt_v_int[i] : 0.0;
         }
         for (int i = tid; i < n * d; i += kSweepThreads) sm.xs[i] = S.x_int[i];
+        if (sep) {
+            const double* __restrict__ gl = S.grid[d - 1];
+            for (int e = tid; e < n * p_last; e += kSweepThreads) {
+                const int i = e / p_last, j = e - i * p_last;
+                const double q = gl[j] - S.x_int[i * d + d - 1];
+                eLast[i * ldl + j] = exp(-0.5 * (q * q));
+            }
+            const long long last_row = (gidx0 + cnt - 1) / p_last;
+            const int nrows = (int)(last_row - row_first) + 1;
+            for (int e = tid; e < n * nrows; e += kSweepThreads) {
+                const int i = e / nrows, r = e - i * nrows;
+                long long rr = row_first + r;
+                double r2 = 0.0;
+                for (int k = d - 2; k >= 0; --k) {
+                    const long long pk = S.p[k];
+                    const double q = S.grid[k][(int)(rr % pk)] - S.x_int[i * d + k];
+                    r2 = fma(q, q, r2);
+                    rr /= pk;
+                }
+                eLead[i * ldr + r] = exp(-0.5 * r2);
+            }
+        }
         __syncthreads();
     }
 
-    const long long loc = (long long)tile * kSweepThreads + tid;
-    const bool valid = loc < S.g_count;
-    const long long gidx = S.g_begin + loc;
     double val = -DBL_MAX * 2.0;  // -inf
     long long idx = LLONG_MAX;
-    int is_nan = 0;
-    if (valid) {
+    int n_nan = 0;
+    // this thread's candidates: loc0 + tid, + 128, ...; (row, j) = (leading row, fastest index) advance without divisions
+    long long row = row_first;
+    int jj = 0;
+    if (!S.points) {
+        const long long g = gidx0 + tid;
+        row = g / p_last;
+        jj = (int)(g - row * p_last);
+    }
+    const bool need_x = (!cached && !sep) || S.cost_variable;
+#pragma unroll 1
+    for (int c = tid; c < cnt; c += kSweepThreads) {
+        const long long loc = loc0 + c, gidx = gidx0 + c;
         double x[CBO_MAX_D];
-        const bool need_x = !cached || S.cost_variable;
-        if (!need_x) {
 #pragma unroll
-            for (int k = 0; k < CBO_MAX_D; ++k) x[k] = 0.0;
-        } else if (S.points) {  // explicit candidates
+        for (int k = 0; k < CBO_MAX_D; ++k) x[k] = 0.0;
+        if (need_x) {
+            if (S.points) {  // explicit candidates
 #pragma unroll
-            for (int k = 0; k < CBO_MAX_D; ++k) x[k] = k < d ? S.points[gidx * d + k] : 0.0;
-        } else if (S.g_total < 0x7fffffffLL) {  // 32-bit index arithmetic (64-bit div/mod is an emulated, long sequence)
-            unsigned gg = (unsigned)gidx;
-#pragma unroll
-            for (int k = CBO_MAX_D - 1; k >= 0; --k) {
-                if (k < d) {
-                    const unsigned pk = (unsigned)S.p[k], q = gg / pk;
-                    x[k] = S.grid[k][gg - q * pk];
-                    gg = q;
-                } else {
-                    x[k] = 0.0;
-                }
-            }
-        } else {
-            long long gg = gidx;
-#pragma unroll
-            for (int k = CBO_MAX_D - 1; k >= 0; --k) {
-                if (k < d) {
-                    const int i = (int)(gg % S.p[k]);
-                    gg /= S.p[k];
-                    x[k] = S.grid[k][i];
-                } else {
-                    x[k] = 0.0;
+                for (int k = 0; k < CBO_MAX_D; ++k) x[k] = k < d ? S.points[gidx * d + k] : 0.0;
+            } else {
+                long long rr = row;
+                x[d - 1] = S.grid[d - 1][jj];
+                for (int k = d - 2; k >= 0; --k) {
+                    const long long pk = S.p[k];
+                    x[k] = S.grid[k][(int)(rr % pk)];
+                    rr /= pk;
                 }
             }
         }
@@ -157,10 +218,12 @@ sweep_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, double best, d
             const double mg = causal ? S.m[loc] : 0.0;
             const double svg = causal ? sqrt(vg) : 0.0;
             double ss;
-            if (n <= 16) posterior_at<16>(sm, n, d, x, svg, tid, mu, ss);
-            else if (n <= 32) posterior_at<32>(sm, n, d, x, svg, tid, mu, ss);
-            else if (n <= 48) posterior_at<48>(sm, n, d, x, svg, tid, mu, ss);
-            else posterior_at<0>(sm, n, d, x, svg, tid, mu, ss);
+            if constexpr (NREG > 0) {
+                if (sep) posterior_sep<NREG>(sm, n, eLast + jj, ldl, eLead + (int)(row - row_first), ldr, svg, mu, ss);
+                else posterior_at<NREG>(sm, n, d, x, svg, tid, mu, ss);
+            } else {
+                posterior_at<0>(sm, n, d, x, svg, tid, mu, ss);
+            }
             mu += mg;
             var = ((1.0 + vg) - ss) + 1e-10;
             if (S.mu) S.mu[loc] = mu;
@@ -180,19 +243,20 @@ sweep_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, double best, d
         const double acq = ei / cost;
         if (S.ei) S.ei[loc] = ei;
         if (S.acq) S.acq[loc] = acq;
-        is_nan = acq != acq;
-        val = is_nan ? val : acq;
-        idx = gidx;
+        if (acq != acq) ++n_nan;
+        else if (better(acq, gidx, val, idx)) { val = acq; idx = gidx; }
+        jj += kSweepThreads;
+        while (jj >= p_last && !S.points) { jj -= p_last; ++row; }
     }
     // first-argmax over the tile
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const double ov = __shfl_xor_sync(0xffffffffu, val, o);
         const long long oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        n_nan += __shfl_xor_sync(0xffffffffu, n_nan, o);
         if (better(ov, oi, val, idx)) { val = ov; idx = oi; }
     }
-    const int nn = __popc(__ballot_sync(0xffffffffu, is_nan));
-    if ((tid & 31) == 0) { red_v[tid >> 5] = val; red_i[tid >> 5] = idx; red_n[tid >> 5] = nn; }
+    if ((tid & 31) == 0) { red_v[tid >> 5] = val; red_i[tid >> 5] = idx; red_n[tid >> 5] = n_nan; }
     __syncthreads();
     if (tid == 0) {
         int nan_total = red_n[0];
@@ -284,6 +348,7 @@ int sweep_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_s
     CBO_REQUIRE(d_tile_best && d_set_best && d_result, "cbo_sweep: NULL output pointer");
     long long total = 0;
     int nmax = 1;
+    size_t tab_doubles = 0;      // the two k* tables of the separable path, or the generic path's [n][threads] workspace
     for (int s = 0; s < num_sets; ++s) {
         const cbo_set_desc& S = h_sets[s];
         CBO_REQUIRE(S.n_int >= 1 && S.n_int <= CBO_MAX_NINT, "cbo_sweep: set %d n_int=%d outside [1,%d]", s, S.n_int, CBO_MAX_NINT);
@@ -293,13 +358,17 @@ int sweep_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_s
         for (int k = 0; k < (S.points ? 0 : S.d); ++k) CBO_REQUIRE(S.grid[k], "cbo_sweep: set %d grid[%d] is NULL", s, k);
         total += host_items(S, kItemsSweep);
         if (S.n_int > nmax) nmax = S.n_int;
+        size_t t = 0;
+        if (!S.posterior_cached && sweep_separable(S)) t = (size_t)S.n_int * ((S.p[S.d - 1] | 1) + (sweep_lead_rows(S) | 1));
+        if (t > tab_doubles) tab_doubles = t;
     }
     CBO_REQUIRE(total < 2147483647LL, "cbo_sweep: too many work items");
     if (total > 0) {
-        const size_t smem = ((size_t)nmax * (nmax + 1) / 2 + 2 * (size_t)nmax + (size_t)nmax * CBO_MAX_D +
-                             (nmax > 48 ? (size_t)nmax * kSweepThreads : 0)) * sizeof(double);
-        if (smem > 48 * 1024) CBO_CUDA(allow_dynamic_smem(sweep_kernel, smem));
-        sweep_kernel<<<(unsigned)total, kSweepThreads, smem, st>>>(d_sets, num_sets, best, (double)task_sign, d_tile_best);
+        if (nmax > 48) tab_doubles = (size_t)nmax * kSweepThreads;     // generic path: [n][threads] solution workspace, no tables
+        const size_t smem = ((size_t)nmax * (nmax + 1) / 2 + 2 * (size_t)nmax + (size_t)nmax * CBO_MAX_D + tab_doubles) * sizeof(double);
+        auto kern = nmax <= 16 ? sweep_kernel<16> : (nmax <= 32 ? sweep_kernel<32> : (nmax <= 48 ? sweep_kernel<48> : sweep_kernel<0>));
+        if (smem > 48 * 1024) CBO_CUDA(allow_dynamic_smem(kern, smem));
+        kern<<<(unsigned)total, kSweepThreads, smem, st>>>(d_sets, num_sets, best, (double)task_sign, d_tile_best);
         note_launch();
         CBO_CUDA(cudaGetLastError());
     }

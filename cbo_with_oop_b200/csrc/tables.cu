@@ -47,10 +47,71 @@ points_table_kernel(const double* __restrict__ x_int, int n_int, int d, const do
     }
 }
 
-int build_tables_impl(const cbo_set_desc* h_sets, int num_sets, cudaStream_t st) {
+// Every table of every set in one launch (needs the descriptors on the device): blockIdx.z = set * (CBO_MAX_D + 1) + table,
+// table == d being the interventional-row table u_int.  Explicit-point sets keep their own launch.
+__global__ void __launch_bounds__(256)
+tables_batched_kernel(const cbo_set_desc* __restrict__ sets) {
+    const cbo_set_desc& S = sets[blockIdx.z / (CBO_MAX_D + 1)];
+    const int k = blockIdx.z % (CBO_MAX_D + 1);
+    if (!computes_prior(S) || S.points || k > S.d) return;
+    const int n_obs = S.n_obs, n_obs_pad = S.n_obs_pad, d = S.d;
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= n_obs_pad) return;
+    const bool live = j < n_obs;
+    if (k < d) {
+        const double x = live ? S.x_obs_int[(size_t)k * n_obs + j] : 0.0, inv_l = 1.0 / S.ls_int[k];
+        const double* __restrict__ coords = S.grid[k];
+        double* __restrict__ out = S.tab[k];
+        for (int i = blockIdx.y; i < S.p[k]; i += gridDim.y) {
+            const double t = (coords[i] - x) * inv_l;
+            out[(size_t)i * n_obs_pad + j] = live ? exp(-0.5 * (t * t)) : 0.0;
+        }
+    } else {
+        double x[CBO_MAX_D], il[CBO_MAX_D];
+#pragma unroll
+        for (int q = 0; q < CBO_MAX_D; ++q) {
+            x[q] = (live && q < d) ? S.x_obs_int[(size_t)q * n_obs + j] : 0.0;
+            il[q] = q < d ? 1.0 / S.ls_int[q] : 0.0;
+        }
+        for (int i = blockIdx.y; i < S.n_int; i += gridDim.y) {
+            double r2 = 0.0;
+#pragma unroll
+            for (int q = 0; q < CBO_MAX_D; ++q) {
+                if (q < d) {
+                    const double t = (S.x_int[i * d + q] - x[q]) * il[q];
+                    r2 += t * t;
+                }
+            }
+            S.u_int[(size_t)i * n_obs_pad + j] = live ? exp(-0.5 * r2) : 0.0;
+        }
+    }
+}
+
+int build_tables_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_sets, cudaStream_t st) {
+    bool batched = d_sets != nullptr && num_sets > 1 && num_sets * (CBO_MAX_D + 1) <= 65535;
+    if (batched) {
+        int npad_max = 0, rows_max = 1;
+        for (int s = 0; s < num_sets; ++s) {
+            const cbo_set_desc& S = h_sets[s];
+            if (!computes_prior(S) || S.points) continue;
+            for (int k = 0; k < S.d; ++k) {
+                CBO_REQUIRE(S.tab[k] && S.grid[k] && S.x_obs_int, "cbo_build_tables: set %d has a NULL table/grid pointer", s);
+                if (S.p[k] > rows_max) rows_max = S.p[k];
+            }
+            CBO_REQUIRE(S.u_int && S.x_int, "cbo_build_tables: set %d has a NULL u_int/x_int pointer", s);
+            if (S.n_int > rows_max) rows_max = S.n_int;
+            if (S.n_obs_pad > npad_max) npad_max = S.n_obs_pad;
+        }
+        if (npad_max > 0) {
+            tables_batched_kernel<<<dim3((unsigned)((npad_max + 255) / 256), (unsigned)(rows_max < 256 ? rows_max : 256),
+                                         (unsigned)(num_sets * (CBO_MAX_D + 1))), 256, 0, st>>>(d_sets);
+            note_launch();
+            CBO_CUDA(cudaGetLastError());
+        }
+    }
     for (int s = 0; s < num_sets; ++s) {
         const cbo_set_desc& S = h_sets[s];
-        if (!computes_prior(S)) continue;
+        if (!computes_prior(S) || (batched && !S.points)) continue;
         const unsigned gx = (S.n_obs_pad + 255) / 256;
         const double il[CBO_MAX_D] = {1.0 / S.ls_int[0], S.d > 1 ? 1.0 / S.ls_int[1] : 0.0, S.d > 2 ? 1.0 / S.ls_int[2] : 0.0,
                                       S.d > 3 ? 1.0 / S.ls_int[3] : 0.0};

@@ -156,7 +156,11 @@ class SweepEngine:
             if pr.computes_prior and pr.x_obs_cond.shape[1] > 0:
                 p_rows = max(p_rows, _round_up(pr.x_obs_int.shape[0], _lib.CBO_NPAD))
                 p_cols = max(p_cols, _round_up(pr.mc_cond.shape[0], _lib.CBO_SPAD))
+        # P scratch of the prior precompute: one buffer per set when that is small (the library then runs every set in one
+        # launch per stage), one shared stream-ordered buffer when the sets are large (0.8 GB each at N = 1e4)
         self.P = self._dev((p_rows * p_cols,)) if p_rows else None
+        n_cond = sum(1 for g in self.active if self.problems[g].computes_prior and self.problems[g].x_obs_cond.shape[1] > 0)
+        self._private_P = p_rows > 0 and n_cond > 1 and n_cond * p_rows * p_cols * 8 <= (1 << 30)
         for li, g in enumerate(self.active):
             pr = self.problems[g]
             d, n = pr.d, pr.x_int.shape[0]
@@ -197,6 +201,8 @@ class SweepEngine:
                 b["pbar"] = self._dev((Np,))
                 b["w"] = self._dev((Np,))
                 b["M"] = self._dev((Np * Np,))
+                if self._private_P and c > 0:
+                    b["P"] = self._dev((Np * _round_up(max(Smc, 1), _lib.CBO_SPAD),))
                 b["m"] = self._dev((gc,))
                 b["v"] = self._dev((gc,))
             self.buf.append(b)
@@ -260,7 +266,7 @@ class SweepEngine:
                 for k in range(d):
                     D.tab[k] = ptr(f"tab{k}")
                 D.u_int, D.pbar, D.w, D.M = ptr("u_int"), ptr("pbar"), ptr("w"), ptr("M")
-                D.P = self.P.data_ptr() if (self.P is not None and c > 0) else None
+                D.P = ptr("P") if "P" in b else (self.P.data_ptr() if (self.P is not None and c > 0) else None)
         A = len(self.active)
         self.d_sets = torch.empty((max(A, 1) * C.sizeof(SetDesc),), dtype=torch.uint8, device=self.device)
         self._descs_dirty = True
@@ -410,14 +416,14 @@ class SweepEngine:
         out.append((name, e0, e1))
 
     def build_tables(self, local_ids=None):
-        h, _, n = self._subset(local_ids)
+        h, dptr, n = self._subset(local_ids)
         if n:
-            _lib.check(self.lib.cbo_build_tables(h, n, self._stream()), "cbo_build_tables")
+            _lib.check(self.lib.cbo_build_tables(h, dptr, n, self._stream()), "cbo_build_tables")
 
     def prior_precompute(self, local_ids=None):
-        h, _, n = self._subset(local_ids)
+        h, dptr, n = self._subset(local_ids)
         if n:
-            _lib.check(self.lib.cbo_prior_precompute(h, n, self._stream()), "cbo_prior_precompute")
+            _lib.check(self.lib.cbo_prior_precompute(h, dptr, n, self._stream()), "cbo_prior_precompute")
 
     def prior_eval(self, which: int, local_ids=None):
         h, dptr, n = self._subset(local_ids)
@@ -586,7 +592,7 @@ class SweepEngine:
             d_desc = torch.frombuffer(bytearray(bytes(h)), dtype=torch.uint8).to(dev)
             dptr, st = C.c_void_p(d_desc.data_ptr()), self._stream()
             if pr.computes_prior:
-                _lib.check(self.lib.cbo_build_tables(h, 1, st), "cbo_build_tables")
+                _lib.check(self.lib.cbo_build_tables(h, dptr, 1, st), "cbo_build_tables")
                 _lib.check(self.lib.cbo_prior_eval(h, dptr, 1, 0, C.c_void_p(self.prior_ws.data_ptr()), self.prior_ws.numel(), st),
                            "cbo_prior_eval")
             if stages == "all":

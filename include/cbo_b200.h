@@ -37,7 +37,7 @@ extern "C" {
 #define CBO_NPAD 128         /* n_obs_pad must be a multiple of this */
 #define CBO_SPAD 16          /* n_mc_pad must be a multiple of this */
 #define CBO_PRIOR_TILE 128   /* grid points per prior-eval work item */
-#define CBO_SWEEP_TILE 128   /* grid points per sweep work item (one thread each) */
+#define CBO_SWEEP_TILE 1024  /* grid points per sweep work item (128 threads, 8 candidates each) */
 
 /* One exploration set.  Index conventions follow SURVEY.md §8(d): the candidate grid is the tensor
  * product of per-dimension coordinate tables, flattened C-order (last dimension fastest). */
@@ -156,13 +156,16 @@ CBO_API int cbo_obs_gp_nll(const cbo_set_desc* h_set, void* d_workspace, size_t 
 
 /* K0. exp tables: tab[k][i][j] = exp(-.5 ((grid[k][i] - x_obs_int[k][j]) / ls_int[k])^2) and
  * u_int[i][j] = exp(-.5 sum_k ((x_int[i][k] - x_obs_int[k][j]) / ls_int[k])^2).
- * Replaces the kernel evaluations inside gp.predict at DoCalculus.py:77 for the intervened columns. */
-CBO_API int cbo_build_tables(const cbo_set_desc* h_sets, int num_sets, void* stream);
+ * Replaces the kernel evaluations inside gp.predict at DoCalculus.py:77 for the intervened columns.
+ * `d_sets` may be NULL; with the descriptors on the device every table of every set is written by ONE launch. */
+CBO_API int cbo_build_tables(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_sets, void* stream);
 
 /* K1a. P, pbar, w, M from the observational GP state and the conditioning samples.
  * Replaces the per-candidate np.hstack + gp.predict set-up of DoCalculus.py:68-89 (done once per
- * observation instead of once per candidate). */
-CBO_API int cbo_prior_precompute(const cbo_set_desc* h_sets, int num_sets, void* stream);
+ * observation instead of once per candidate).
+ * `d_sets` may be NULL; with the descriptors on the device and a P buffer per set (no two sets sharing one) all sets
+ * go through one launch per stage instead of two launches per set. */
+CBO_API int cbo_prior_precompute(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_sets, void* stream);
 
 /* K1b. causal prior m(x) = u.w, v(x) = s2 + noise - u^T M u.
  * which = 0: on the rank's slice of the tensor grid, or on explicit points (writes m, v).  FP64 tensor pipe (DMMA);

@@ -50,12 +50,12 @@ def test_struct_mirror_and_version(lib):
 def test_argument_validation_reports_through_last_error(lib):
     from cbo_with_oop_b200 import _lib
     h = (_lib.SetDesc * 1)()
-    assert lib.cbo_build_tables(h, 1, None) == -1
+    assert lib.cbo_build_tables(h, None, 1, None) == -1
     assert b"d=0" in lib.cbo_last_error()
     h[0].d, h[0].n_int, h[0].p[0], h[0].g_total, h[0].g_count = 1, 5, 10, 10, 10
     h[0].causal, h[0].n_obs, h[0].n_obs_pad = 1, 100, 100          # pad not a multiple of 128
     h[0].cost_fix = 1.0
-    assert lib.cbo_prior_precompute(h, 1, None) == -1
+    assert lib.cbo_prior_precompute(h, None, 1, None) == -1
     assert b"n_obs_pad" in lib.cbo_last_error()
     h[0].g_total = 11
     assert lib.cbo_sweep(h, None, 1, 0.0, 1, None, None, None, None) == -1
