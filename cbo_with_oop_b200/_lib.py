@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcbo_b200.so")
+LIB_PATH = os.environ.get("CBO_B200_LIB") or os.path.join(HERE, "libcbo_b200.so")   # (the override is for kernel experiments)
 
 CBO_ABI_VERSION = 6
 CBO_MAX_D = 4
@@ -55,8 +55,18 @@ EXPORTS = [
     "cbo_prior_eval_flops",
     "cbo_obs_gp_fit", "cbo_obs_gp_nll",
     "cbo_build_tables", "cbo_prior_precompute", "cbo_prior_eval", "cbo_posterior_fit", "cbo_sweep",
-    "cbo_argmax_combine",
+    "cbo_argmax_combine", "cbo_sem_eval",
 ]
+CBO_SEM_MAX_NODES, CBO_SEM_MAX_TERMS, CBO_SEM_BLOCKS = 16, 96, 64
+SEM_FUNCS = {"id": 0, "exp": 1, "cos": 2, "sin": 3, "square": 4}
+
+
+class SemTerm(C.Structure):
+    _fields_ = [("src", C.c_int32), ("func", C.c_int32), ("coef", C.c_double), ("scale", C.c_double)]
+
+
+class SemNode(C.Structure):
+    _fields_ = [("first_term", C.c_int32), ("num_terms", C.c_int32), ("constant", C.c_double)]
 
 _lib = None
 
@@ -104,6 +114,8 @@ def load() -> C.CDLL:
     lib.cbo_sweep.argtypes = [P, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_void_p]
     lib.cbo_argmax_combine.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.cbo_sem_eval.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p,
+                                 C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     for name in EXPORTS[10:]:
         getattr(lib, name).restype = C.c_int
     if lib.cbo_abi_version() != CBO_ABI_VERSION:

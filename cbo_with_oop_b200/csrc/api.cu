@@ -70,6 +70,8 @@ int argmax_combine_impl(const cbo_set_best*, int, int, cbo_set_best*, cbo_sweep_
 size_t obs_gp_workspace_bytes_impl(const cbo_set_desc*, int);
 int obs_gp_fit_impl(const cbo_set_desc*, int, double, void*, size_t, int32_t*, cudaStream_t);
 int obs_gp_nll_impl(const cbo_set_desc*, void*, size_t, double*, cudaStream_t);
+int sem_eval_impl(const cbo_sem_node*, int, const cbo_sem_term*, int, const double*, int, long long, const int32_t*, const double*, int,
+                  int, double*, double*, cudaStream_t);
 
 }  // namespace cbo
 
@@ -179,6 +181,13 @@ int cbo_argmax_combine(const cbo_set_best* d_gathered, int num_ranks, int num_se
                        cbo_sweep_result* d_result, void* stream) {
     CBO_REQUIRE(d_set_best && d_result, "cbo_argmax_combine: NULL output pointer");
     return argmax_combine_impl(d_gathered, num_ranks, num_sets, d_set_best, d_result, (cudaStream_t)stream);
+}
+
+int cbo_sem_eval(const cbo_sem_node* d_nodes, int num_nodes, const cbo_sem_term* d_terms, int num_terms, const double* d_noise,
+                 int num_noise, long long num_samples, const int32_t* d_do_mask, const double* d_do_value, int batch, int target_node,
+                 double* d_partials, double* d_mean, void* stream) {
+    return sem_eval_impl(d_nodes, num_nodes, d_terms, num_terms, d_noise, num_noise, num_samples, d_do_mask, d_do_value, batch,
+                         target_node, d_partials, d_mean, (cudaStream_t)stream);
 }
 
 }  // extern "C"

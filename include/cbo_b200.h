@@ -219,6 +219,24 @@ CBO_API int cbo_sweep(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, in
 CBO_API int cbo_argmax_combine(const cbo_set_best* d_gathered, int num_ranks, int num_sets,
                        cbo_set_best* d_set_best, cbo_sweep_result* d_result, void* stream);
 
+/* K6. Ground truth of an intervention: E[target | do(...)] of a structural equation model by Monte Carlo.
+ * Replaces compute_interventions / sample_from_model / intervene_dict (graph_functions.py:8-77: 100 000 samples in a Python
+ * loop per intervention; the function reseeds with seed 1 on every call, so the noise matrix is a constant of the run and
+ * stays on the device).  The SEM is a program over nodes in topological order:
+ *   value[i] = constant_i + sum_t coef_t * f_t(scale_t * source_t) ,  source_t = noise[src] when src < num_noise, else
+ *   value[src - num_noise] (an earlier node);  an intervened node (do_mask) takes do_value instead.
+ * d_noise: (num_noise, num_samples) row-major; d_do_mask / d_do_value: (batch, num_nodes); d_partials: scratch of
+ * batch * CBO_SEM_BLOCKS doubles; d_mean: (batch) Monte-Carlo means of the target node (deterministic summation order). */
+#define CBO_SEM_MAX_NODES 16
+#define CBO_SEM_MAX_TERMS 96
+#define CBO_SEM_BLOCKS 64
+enum { CBO_SEM_ID = 0, CBO_SEM_EXP = 1, CBO_SEM_COS = 2, CBO_SEM_SIN = 3, CBO_SEM_SQUARE = 4 };
+typedef struct cbo_sem_term { int32_t src; int32_t func; double coef; double scale; } cbo_sem_term;
+typedef struct cbo_sem_node { int32_t first_term; int32_t num_terms; double constant; } cbo_sem_node;
+CBO_API int cbo_sem_eval(const cbo_sem_node* d_nodes, int num_nodes, const cbo_sem_term* d_terms, int num_terms,
+                         const double* d_noise, int num_noise, long long num_samples, const int32_t* d_do_mask,
+                         const double* d_do_value, int batch, int target_node, double* d_partials, double* d_mean, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

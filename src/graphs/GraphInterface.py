@@ -40,6 +40,16 @@ class GraphInterface(abc.ABC):
     def get_interventional_ranges():
         ...
 
+    # ---- the SEM as a device program (cbo_with_oop_b200/sem.py) -------------------------
+    @staticmethod
+    def _draw_gaussian_noise(num_nodes):
+        """Noise of a SEM whose only randomness is `epsilon`: the host function's draw, np.random.seed(seed) followed by
+        randn(num_samples, num_nodes) (graph_functions.compute_interventions), one row per node."""
+        def draw(num_samples, intervened, seed):
+            np.random.seed(seed)
+            return np.ascontiguousarray(np.random.randn(num_samples, num_nodes).T)
+        return draw
+
     # ---- naming helpers (reference GraphInterface.py:29-43) -----------------------------------------
     @staticmethod
     def get_function_name(interventions):

@@ -47,6 +47,20 @@ class CompleteGraph(GraphInterface):
                                                          + epsilon[7])
         return sem
 
+    def device_sem(self):
+        """define_sem() as a program for cbo_sem_eval (term = (source, func, coef, scale): coef * func(scale * source))."""
+        e = [f"e{i}" for i in range(9)]
+        one = lambda src: (src, "id", 1.0, 1.0)
+        return {"noise": e, "draw": self._draw_gaussian_noise(9),
+                "nodes": [("U1", 0.0, [one("e0")]), ("U2", 0.0, [one("e1")]), ("F", 0.0, [one("e8")]),
+                          ("A", 0.0, [("F", "square", 1.0, 1.0), one("U1"), one("e2")]),
+                          ("B", 0.0, [one("U2"), one("e3")]),
+                          ("C", 0.0, [("B", "exp", 1.0, -1.0), one("e4")]),
+                          ("D", 0.0, [("C", "exp", 1.0 / 10.0, -1.0), one("e5")]),
+                          ("E", 0.0, [("A", "cos", 1.0, 1.0), ("C", "id", 1.0 / 10.0, 1.0), one("e6")]),
+                          ("Y", 0.0, [("D", "cos", 1.0, 1.0), ("D", "id", -1.0 / 5.0, 1.0), ("E", "sin", 1.0, 1.0),
+                                      ("E", "id", -1.0 / 4.0, 1.0), one("U1"), ("U2", "exp", 1.0, -1.0), one("e7")])]}
+
     @staticmethod
     def get_exploration_set(set_name):
         mis = [["B"], ["D"], ["E"], ["B", "D"], ["B", "E"], ["D", "E"]]

@@ -82,6 +82,25 @@ class CoralGraph(GraphInterface):
             sem[child] = self._linear(child)
         return sem
 
+    def device_sem(self):
+        """define_sem() as a program for cbo_sem_eval.  The two stochastic roots are per-sample inputs drawn on the host
+        exactly as compute_interventions draws them: np.random.seed(seed), randn(num_samples, 11) (unused by the linear
+        equations but it advances the stream), then N from the Gaussian mixture unless N is intervened, then L from the
+        gamma law -- both through the global NumPy stream, as define_sem()'s f_n / f_l do."""
+        def draw(num_samples, intervened, seed):
+            np.random.seed(seed)
+            np.random.randn(num_samples, 11)
+            n = np.zeros(num_samples) if "N" in intervened else self.dist_nutrients_pc1.sample(num_samples)[0][:, 0]
+            light = self.dist_Light.rvs(num_samples)
+            return np.vstack([n, light])
+
+        nodes = [("N", 0.0, [("n_draw", "id", 1.0, 1.0)]), ("L", 0.0, [("l_draw", "id", 1.0, 1.0)])]
+        for child in ["TE", "C", "S", "T", "D", "P", "O", "CO", "Y"]:
+            reg = self.regressions[child]
+            coef, icpt = np.asarray(reg.coef_).reshape(-1), float(np.asarray(reg.intercept_).reshape(-1)[0])
+            nodes.append((child, icpt, [(p, "id", float(c), 1.0) for c, p in zip(coef, self.parents[child])]))
+        return {"noise": ["n_draw", "l_draw"], "draw": draw, "nodes": nodes}
+
     @staticmethod
     def get_exploration_set(set_name):
         mis_1 = [["N"], ["O"], ["C"], ["T"], ["D"]]

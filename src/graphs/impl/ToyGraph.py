@@ -30,6 +30,13 @@ class ToyGraph(GraphInterface):
 
         return OrderedDict([("X", f_x), ("Z", f_z), ("Y", f_y)])
 
+    def device_sem(self):
+        """define_sem() as a program for cbo_sem_eval (term = (source, func, coef, scale): coef * func(scale * source))."""
+        return {"noise": ["e0", "e1", "e2"], "draw": self._draw_gaussian_noise(3),
+                "nodes": [("X", 0.0, [("e0", "id", 1.0, 1.0)]),
+                          ("Z", 0.0, [("X", "exp", 1.0, -1.0), ("e1", "id", 1.0, 1.0)]),
+                          ("Y", 0.0, [("Z", "cos", 1.0, 1.0), ("Z", "exp", -1.0, -1.0 / 20.0), ("e2", "id", 1.0, 1.0)])]}
+
     @staticmethod
     def get_exploration_set(set_name):
         return [["X"], ["Z"]]

@@ -42,10 +42,28 @@ def define_initial_data_cbo(interventional_data, num_interventions, exploration_
     (reference :44-115).  interventional_data[j] = [k, name_1..name_k, X (p,k), y (p,1)]."""
     pick = np.min if task == "min" else np.max
     data_x_list, data_y_list, opt_list = [], [], []
+    # Rows are matched to exploration sets by their variable NAMES: the reference matches by position
+    # (cbo_functions.py:51-52), which hands a set another set's design whenever the shipped row order differs from the
+    # exploration set in use (complete_graph MIS: SURVEY.md Appendix B #10; any POMIS list that skips a MIS entry).
+    by_name = {}
+    for row in interventional_data:
+        k = int(row[0])
+        by_name[tuple(str(v) for v in row[1:1 + k])] = row
     for j in range(len(exploration_set)):
-        row = interventional_data[j]
+        key = tuple(str(v) for v in exploration_set[j])
+        perm = None
+        if key in by_name:
+            row = by_name[key]
+        else:   # same variables in another order: take that row and permute its columns
+            match = [kk for kk in by_name if sorted(kk) == sorted(key)]
+            if not match:
+                raise KeyError(f"no interventional data for exploration set {list(key)} (rows: {sorted(by_name)})")
+            row = by_name[match[0]]
+            perm = [match[0].index(v) for v in key]
         k = int(row[0])
         x = np.asarray(row[k + 1], np.float64)
+        if perm is not None:
+            x = x.reshape(len(x), -1)[:, perm]
         y = np.asarray(row[-1], np.float64)
         x = x.reshape(len(x), -1)
         y = y.reshape(len(y), -1)[:, :1]

@@ -100,3 +100,20 @@ def test_pair_and_general_paths_agree(cuda_engine_ready):
     m_gen, v_gen = eng.fetch("m", 0), eng.fetch("v", 0)
     assert rel_err(m_pair, m_gen, 1e-6).max() <= 1e-9
     assert rel_err(v_pair, v_gen, 1e-6).max() <= 1e-9
+
+
+def test_pair_path_first_launch_is_repeatable(cuda_engine_ready):
+    """The first evaluation on a fresh workspace must equal the second bit for bit (the summation order is fixed).  Guards the
+    second-level accumulator slots in shared memory: an earlier version read them before their first write and was wrong, on
+    the first launch only, in the one warp that owned a 4 x 4 share of the 13 x 13 tile."""
+    kw, _ = make_case(seed=231, N=100, d=3, c=2, n=8, p=(148, 100, 100), ard=False)
+    for attempt in range(2):          # two fresh engines: fresh shared memory / workspace contents each time
+        eng = _engine([kw])
+        assert _pair_items(eng) >= eng.num_sms
+        eng.build_tables(), eng.prior_precompute(), eng.prior_eval(0)
+        m0, v0 = eng.fetch("m", 0).copy(), eng.fetch("v", 0).copy()
+        for _ in range(2):
+            eng.prior_eval(0)
+            np.testing.assert_array_equal(eng.fetch("m", 0), m0)
+            np.testing.assert_array_equal(eng.fetch("v", 0), v0)
+        del eng

@@ -154,3 +154,27 @@ def test_agent_constructor_and_policy_pieces(in_tmp):
     assert cbo.monitor.type_trial == [0] and cbo.monitor.global_opt[-1] == cbo.monitor.global_opt[0]
     pr = cbo.do_calculus.set_problem(4)                                      # ['B', 'E'] -> GP on B, E, C, A
     assert pr.x_obs_int.shape == (120, 2) and pr.x_obs_cond.shape == (120, 2) and pr.g_total == 400 and pr.cost_fix == 2.0
+
+
+def test_interventional_rows_follow_the_exploration_set_by_name(in_tmp):
+    """The initial interventional data of every exploration set is the shipped row with the same variable names, whatever
+    list of sets is in use (reference matches by position, cbo_functions.py:51-52: with complete_graph's POMIS list the
+    set ['D', 'E'] would start from the ['B', 'E'] design)."""
+    from src.CBO import CBO
+    from src.DataLoader import DataLoader
+    data = DataLoader("complete_graph", 100)
+    shipped = {tuple(str(v) for v in row[1:1 + int(row[0])]): np.asarray(row[int(row[0]) + 1], np.float64).reshape(len(row[-1]), -1)
+               for row in data.interventions}
+    for es in ("MIS", "POMIS"):
+        np.random.seed(9)
+        cbo = CBO(make_args(exploration_set=es), data, verbose=False)
+        assert cbo.exploration_set == data.graph.get_exploration_set(es)
+        for s, variables in enumerate(cbo.exploration_set):
+            design = shipped[tuple(variables)]
+            x = np.asarray(cbo.monitor.data_x[s])
+            assert x.shape == (10, len(variables))
+            for row in x:       # every initial row of the set comes from the set's OWN shipped design
+                assert np.any(np.all(np.isclose(design, row[None, :]), axis=1)), (es, variables)
+    from src.utils_functions.cbo_functions import define_initial_data_cbo
+    with pytest.raises(KeyError):
+        define_initial_data_cbo(data.interventions, 10, [["B"], ["F"]], 0, "min")
