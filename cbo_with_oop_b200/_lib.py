@@ -55,7 +55,7 @@ EXPORTS = [
     "cbo_prior_eval_flops",
     "cbo_obs_gp_fit", "cbo_obs_gp_nll",
     "cbo_build_tables", "cbo_prior_precompute", "cbo_prior_eval", "cbo_posterior_fit", "cbo_sweep",
-    "cbo_argmax_combine", "cbo_sem_eval",
+    "cbo_argmax_combine", "cbo_sem_eval", "cbo_refresh_trial",
 ]
 CBO_SEM_MAX_NODES, CBO_SEM_MAX_TERMS, CBO_SEM_BLOCKS = 16, 96, 64
 SEM_FUNCS = {"id": 0, "exp": 1, "cos": 2, "sin": 3, "square": 4}
@@ -114,6 +114,8 @@ def load() -> C.CDLL:
     lib.cbo_sweep.argtypes = [P, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_void_p]
     lib.cbo_argmax_combine.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.cbo_refresh_trial.argtypes = [P, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]
     lib.cbo_sem_eval.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p,
                                  C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     for name in EXPORTS[10:]:

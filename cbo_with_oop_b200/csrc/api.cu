@@ -70,6 +70,7 @@ int argmax_combine_impl(const cbo_set_best*, int, int, cbo_set_best*, cbo_sweep_
 size_t obs_gp_workspace_bytes_impl(const cbo_set_desc*, int);
 int obs_gp_fit_impl(const cbo_set_desc*, int, double, void*, size_t, int32_t*, cudaStream_t);
 int obs_gp_nll_impl(const cbo_set_desc*, void*, size_t, double*, cudaStream_t);
+int int_rows_table_impl(const cbo_set_desc&, cudaStream_t);
 int sem_eval_impl(const cbo_sem_node*, int, const cbo_sem_term*, int, const double*, int, long long, const int32_t*, const double*, int,
                   int, double*, double*, cudaStream_t);
 
@@ -175,6 +176,28 @@ int cbo_sweep(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_se
     if (int rc = validate_sets(h_sets, num_sets)) return rc;
     CBO_REQUIRE(d_sets != nullptr, "cbo_sweep: d_sets is NULL");
     return sweep_impl(h_sets, d_sets, num_sets, best, task_sign, d_tile_best, d_set_best, d_result, (cudaStream_t)stream);
+}
+
+int cbo_refresh_trial(const cbo_set_desc* h_sets, cbo_set_desc* d_sets, int num_sets, int refit_set, double best, int task_sign,
+                      void* d_workspace, size_t workspace_bytes, cbo_set_best* d_tile_best, cbo_set_best* d_set_best,
+                      cbo_sweep_result* d_result, void* stream) {
+    if (int rc = validate_sets(h_sets, num_sets)) return rc;
+    CBO_REQUIRE(d_sets != nullptr, "cbo_refresh_trial: d_sets is NULL");
+    CBO_REQUIRE(refit_set >= -1 && refit_set < num_sets, "cbo_refresh_trial: refit_set=%d outside [-1,%d)", refit_set, num_sets);
+    cudaStream_t st = (cudaStream_t)stream;
+    // the descriptors carry this trial's flags (n_int, int_row_begin, posterior_cached): one small host -> device copy
+    CBO_CUDA(cudaMemcpyAsync(d_sets, h_sets, (size_t)num_sets * sizeof(cbo_set_desc), cudaMemcpyHostToDevice, st));
+    if (refit_set >= 0) {
+        const cbo_set_desc* h = h_sets + refit_set;
+        const cbo_set_desc* d = d_sets + refit_set;
+        CBO_REQUIRE(!h->posterior_cached, "cbo_refresh_trial: the refitted set cannot be marked posterior_cached");
+        if (computes_prior(*h)) {
+            if (int rc = int_rows_table_impl(*h, st)) return rc;
+            if (int rc = prior_eval_impl(h, d, 1, 1, d_workspace, workspace_bytes, st)) return rc;
+        }
+        if (int rc = posterior_fit_impl(h, d, 1, st)) return rc;
+    }
+    return sweep_impl(h_sets, d_sets, num_sets, best, task_sign, d_tile_best, d_set_best, d_result, st);
 }
 
 int cbo_argmax_combine(const cbo_set_best* d_gathered, int num_ranks, int num_sets, cbo_set_best* d_set_best,

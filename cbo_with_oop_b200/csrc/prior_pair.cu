@@ -9,9 +9,9 @@
 //                        producer : one elected thread; per 16-deep stage three TMA bulk copies (A slab, B slab, 16 scale
 //                                   values) completing on the stage's mbarrier; 5-stage ring carried across items, so the
 //                                   next item's first slabs arrive while the consumers store the current item's results.
-//                        consumers: 16 warps, each a rectangle of the LIVE 8 x 8 blocks of the tile (13 x 13 at p = 100:
-//                                   16 rectangles of at most 12 blocks, the four schedulers carrying 42/42/42/43
-//                                   blocks); per k4 step NR + NC conflict-free
+//                        consumers: 8 warps in a 2 x 4 arrangement over the LIVE 8 x 8 blocks of the tile (13 x 13 at
+//                                   p = 100: 7|6 row blocks x 4|3|3|3 column blocks, mirrored in the second row half so
+//                                   the four schedulers carry 46/39/39/45 blocks); per k4 step NR + NC conflict-free
 //                                   LDS.64, NC DMULs (the scale row enters through the B fragment) and NR x NC DMMA.8x8x4.
 //                                   After the R pair columns the accumulators ARE u^T M u: v is stored straight from the
 //                                   fragments; the N mean columns follow in the same ring and m is stored the same way.
@@ -38,6 +38,7 @@ struct PairLaunch {
 constexpr int kPairStages = 5;
 constexpr int kPairTile = kPairChunkRows * kBK;              // doubles of one operand slab buffer (13 KB)
 constexpr int kPairStageDoubles = 2 * kPairTile + kBK;       // A slab, B slab, 16 scale values
+constexpr int kPairNCons = 256, kPairNT = kPairNCons + 128;  // 8 consumer warps + one producer warpgroup
 // Second-level accumulators: the reduction runs over 5e3 .. 3.3e4 pair columns whose partial sums are orders of magnitude
 // larger than the result (u^T M u cancels to 1e-3 .. 1e-8 of its terms on the shipped data), and a single FP64
 // accumulator chain of that length loses ~sqrt(length) more than the general kernel's N-long chains do (measured on the
@@ -49,10 +50,8 @@ constexpr int kPairAcc2Doubles = kPairBlocks * 64;
 constexpr size_t kPairSmem = ((size_t)kPairStages * kPairStageDoubles + kPairAcc2Doubles) * sizeof(double) +
                              2 * kPairStages * sizeof(uint64_t) + 16;
 static_assert(kPairSmem <= 232448, "shared memory of one CTA");
-constexpr int kPairNCons = 512, kPairNT = kPairNCons + 32;   // 16 consumer warps + one producer warp, 96 registers each
-// (No setmaxnreg here: the largest share of a warp is 12 blocks = 48 accumulator registers, which fits the launch
-// allocation.  A first 16-warp version that grew the consumers to 112 registers with setmaxnreg.inc returned wrong sums in
-// exactly the one warp that used registers >= 96, on the first launch only -- see DESIGN.md; this layout needs none.)
+constexpr int kPairProdRegs = 40, kPairConsRegs = 232;
+static_assert(128 * kPairProdRegs + kPairNCons * kPairConsRegs <= kPairNT * ((65536 / kPairNT) / 8 * 8), "setmaxnreg budget");
 
 // ---------------------------------------------------------------------------------------------------------------------
 // pair tables.  grid = (slab groups, sets of the launch, 3 tables: A, B, scale); a warp owns one 16-deep slab at a time:
@@ -141,91 +140,93 @@ __device__ __forceinline__ PairItem decode_pair_item(const cbo_set_desc* __restr
     return it;
 }
 
-// A warp's share of the tile: a rectangle of NR x NC live 8 x 8 blocks at (row0, col0).  Accumulators in registers,
-// second-level slots in shared memory (tile block (r, c) -> (r * CB + c), one double2 per lane).
-// Register discipline: the k loop keeps nothing live but the accumulators, two fragment offsets and the ring state; the
-// second-level slot addresses and everything the final store needs (the item's grid position, the set's output pointers)
-// are recomputed where they are used.
+// Consumer side of one item for a warp that owns NR x NC live 8 x 8 blocks starting at (row0, col0) of the tile.
 template <int NR, int NC>
-struct PairShare {
-    static constexpr bool kLive = NR > 0 && NC > 0;
-    double acc[kLive ? NR : 1][kLive ? NC : 1][2];
-
-    __device__ __forceinline__ void zero() {
-        if constexpr (kLive) {
+__device__ __forceinline__ void pair_consume(const PairItem& it, const double* __restrict__ smem, double* __restrict__ acc2,
+                                             uint64_t* full, uint64_t* empty, int& stage, unsigned& phase, int lane, int row0,
+                                             int col0, int CB) {
+    if constexpr (NR == 0 || NC == 0) {   // no live block: walk the ring so that the arrival counts match
+#pragma unroll 1
+        for (int s = 0; s < it.Kslabs; ++s) {
+            mbar_wait(&full[stage], phase);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+            if (++stage == kPairStages) { stage = 0; phase ^= 1u; }
+        }
+        return;
+    } else {
+        const cbo_set_desc& S = *it.S;
+        const int CRa = it.CRa, CRb = it.CRb;
+        const int aoff = (row0 << 2) + lane, boff = (col0 << 2) + lane;
+        // this thread's second-level slots: block (mi, ni) of the warp -> tile block ((row0/8 + mi) * CB + col0/8 + ni)
+        double2* const my2 = reinterpret_cast<double2*>(acc2) + ((row0 >> 3) * CB + (col0 >> 3)) * 32 + lane;
+        double acc[NR][NC][2];
+#pragma unroll 1
+        for (int part = 0; part < 2; ++part) {     // 0: the pair columns -> v ; 1: the mean columns -> m
 #pragma unroll
             for (int mi = 0; mi < NR; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < NC; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-        }
-    }
-    // one k4 step: NR + NC conflict-free LDS.64, NC DMULs (the scale row enters through the B fragments), NR x NC DMMA.8x8x4.
-    // pa / pb: this lane's fragment addresses of the k4 group (row0 / col0 folded in).
-    __device__ __forceinline__ void step(const double* __restrict__ pa, const double* __restrict__ pb, double sc) {
-        if constexpr (kLive) {
-            double a[NR], b[NC];
+            const int nslab = part == 0 ? it.Rslabs : it.Kslabs - it.Rslabs;
+            int since = 0;
+            bool have2 = false;
+#pragma unroll 1
+            for (int s = 0; s < nslab; ++s) {
+                mbar_wait(&full[stage], phase);
+                const double* __restrict__ sA = smem + (size_t)stage * kPairStageDoubles;
+                const double* __restrict__ sB = sA + kPairTile;
+                const double* __restrict__ sS = sB + kPairTile;
 #pragma unroll
-            for (int mi = 0; mi < NR; ++mi) a[mi] = pa[mi * 32];
+                for (int kb = 0; kb < kBK / 4; ++kb) {
+                    const double sc = sS[kb * 4 + (lane & 3)];
+                    double a[NR], b[NC];
 #pragma unroll
-            for (int ni = 0; ni < NC; ++ni) b[ni] = pb[ni * 32] * sc;
+                    for (int mi = 0; mi < NR; ++mi) a[mi] = sA[((kb * CRa + mi * 8) << 2) + aoff];
 #pragma unroll
-            for (int mi = 0; mi < NR; ++mi)
+                    for (int ni = 0; ni < NC; ++ni) b[ni] = sB[((kb * CRb + ni * 8) << 2) + boff] * sc;
 #pragma unroll
-                for (int ni = 0; ni < NC; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
-        }
-    }
-    // second-level slots: zeroed at the start of a part, then the register accumulators are folded in and restarted
-    __device__ __forceinline__ void zero_slots(double* acc2, int row0, int col0, int CB, int lane) {
-        if constexpr (kLive) {
-            double2* my2 = reinterpret_cast<double2*>(acc2) + ((row0 >> 3) * CB + (col0 >> 3)) * 32 + lane;
+                    for (int mi = 0; mi < NR; ++mi)
 #pragma unroll
-            for (int mi = 0; mi < NR; ++mi)
-#pragma unroll
-                for (int ni = 0; ni < NC; ++ni) my2[(mi * CB + ni) * 32] = make_double2(0.0, 0.0);
-        }
-    }
-    __device__ __forceinline__ void flush(double* acc2, int row0, int col0, int CB, int lane) {
-        if constexpr (kLive) {
-            double2* my2 = reinterpret_cast<double2*>(acc2) + ((row0 >> 3) * CB + (col0 >> 3)) * 32 + lane;
-#pragma unroll
-            for (int mi = 0; mi < NR; ++mi)
-#pragma unroll
-                for (int ni = 0; ni < NC; ++ni) {
-                    double2* p2 = my2 + (mi * CB + ni) * 32;
-                    double2 o = *p2;
-                    o.x += acc[mi][ni][0], o.y += acc[mi][ni][1];
-                    *p2 = o;
-                    acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+                        for (int ni = 0; ni < NC; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
                 }
-        }
-    }
-    __device__ __forceinline__ void gather(const double* acc2, int row0, int col0, int CB, int lane) {
-        if constexpr (kLive) {
-            const double2* my2 = reinterpret_cast<const double2*>(acc2) + ((row0 >> 3) * CB + (col0 >> 3)) * 32 + lane;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[stage]);
+                if (++stage == kPairStages) { stage = 0; phase ^= 1u; }
+                if (++since == kPairFlush && s + 1 < nslab) {
 #pragma unroll
-            for (int mi = 0; mi < NR; ++mi)
+                    for (int mi = 0; mi < NR; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < NC; ++ni) {
-                    const double2 o = my2[(mi * CB + ni) * 32];
-                    acc[mi][ni][0] += o.x, acc[mi][ni][1] += o.y;
+                        for (int ni = 0; ni < NC; ++ni) {
+                            double2* p2 = my2 + (mi * CB + ni) * 32;
+                            double2 o = have2 ? *p2 : make_double2(0.0, 0.0);
+                            o.x += acc[mi][ni][0], o.y += acc[mi][ni][1];
+                            *p2 = o;
+                            acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+                        }
+                    have2 = true, since = 0;
                 }
-        }
-    }
-    // straight from the fragments: lane (g, t) holds C[g][2t], C[g][2t+1] of every block
-    __device__ __forceinline__ void store(const PairItem& it, int part, int lane, int row0, int col0) const {
-        if constexpr (kLive) {
-            const cbo_set_desc& S = *it.S;
+            }
+            if (have2) {
+#pragma unroll
+                for (int mi = 0; mi < NR; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < NC; ++ni) {
+                        const double2 o = my2[(mi * CB + ni) * 32];
+                        acc[mi][ni][0] += o.x, acc[mi][ni][1] += o.y;
+                    }
+            }
+            // straight from the fragments: lane (g, t) holds C[g][2t], C[g][2t+1] of every block
             double* __restrict__ out = part == 0 ? S.v : S.m;
             const double sn = S.s2 + S.noise;
             const long long gb = S.g_begin, gc = S.g_count;
 #pragma unroll
             for (int mi = 0; mi < NR; ++mi) {
-                const int ia = it.ca * it.CRa + row0 + mi * 8 + (lane >> 2);
+                const int ia = it.ca * CRa + row0 + mi * 8 + (lane >> 2);
                 if (ia >= it.pa) continue;
                 const long long base = ((long long)it.s * it.pa + ia) * it.pb - gb;
 #pragma unroll
                 for (int ni = 0; ni < NC; ++ni) {
-                    const int ib = it.cb * it.CRb + col0 + ni * 8 + 2 * (lane & 3);
+                    const int ib = it.cb * CRb + col0 + ni * 8 + 2 * (lane & 3);
 #pragma unroll
                     for (int x = 0; x < 2; ++x) {
                         const long long loc = base + ib + x;
@@ -234,50 +235,6 @@ struct PairShare {
                 }
             }
         }
-    }
-};
-
-// Consumer side of one item for one warp.  A warp without live blocks still walks the ring so that the arrival counts match.
-template <int NR, int NC>
-__device__ __forceinline__ void pair_consume(const cbo_set_desc* __restrict__ sets, const PairLaunch& L, const double* __restrict__ area,
-                                             int item, const double* __restrict__ smem, double* __restrict__ acc2, uint64_t* full,
-                                             uint64_t* empty, int& stage, unsigned& phase, int lane, int row0, int col0, int CB) {
-    using Share = PairShare<NR, NC>;
-    Share A;
-    int CRa, CRb, Rslabs, Kslabs;
-    {
-        const PairItem it = decode_pair_item(sets, L, area, item);
-        CRa = it.CRa, CRb = it.CRb, Rslabs = it.Rslabs, Kslabs = it.Kslabs;
-    }
-    const int aoff = (row0 << 2) + lane, boff = (col0 << 2) + lane;
-#pragma unroll 1
-    for (int part = 0; part < 2; ++part) {     // 0: the pair columns -> v ; 1: the mean columns -> m
-        A.zero();
-        A.zero_slots(acc2, row0, col0, CB, lane);
-        const int nslab = part == 0 ? Rslabs : Kslabs - Rslabs;
-        int since = 0;
-#pragma unroll 1
-        for (int s = 0; s < nslab; ++s) {
-            mbar_wait(&full[stage], phase);
-            __syncwarp();
-            if constexpr (Share::kLive) {
-                const double* __restrict__ sA = smem + (size_t)stage * kPairStageDoubles + aoff;
-                const double* __restrict__ sB = smem + (size_t)stage * kPairStageDoubles + kPairTile + boff;
-                const double* __restrict__ sS = smem + (size_t)stage * kPairStageDoubles + 2 * kPairTile + (lane & 3);
-#pragma unroll
-                for (int kb = 0; kb < kBK / 4; ++kb) A.step(sA + ((kb * CRa) << 2), sB + ((kb * CRb) << 2), sS[kb * 4]);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[stage]);
-            if (++stage == kPairStages) { stage = 0; phase ^= 1u; }
-            if (Share::kLive && ++since == kPairFlush && s + 1 < nslab) {
-                A.flush(acc2, row0, col0, CB, lane);
-                since = 0;
-            }
-        }
-        A.gather(acc2, row0, col0, CB, lane);
-        const PairItem it = decode_pair_item(sets, L, area, item);   // re-decoded here: nothing of it is live in the k loop
-        A.store(it, part, lane, row0, col0);
     }
 }
 
@@ -300,8 +257,8 @@ prior_pair_kernel(const cbo_set_desc* __restrict__ sets, const __grid_constant__
     int stage = 0;          // ring position, carried across items: producer and consumers advance identically
     unsigned phase = 0;
     if (warp >= kPairNCons / 32) {
-        // =============================== PRODUCER WARP (one elected thread works) ===============================
-        if (lane == 0) {
+        setmaxnreg_dec<kPairProdRegs>();
+        if (warp == kPairNCons / 32 && lane == 0) {
 #pragma unroll 1
             for (int item = blockIdx.x; item < L.total_items; item += gridDim.x) {
                 const PairItem it = decode_pair_item(sets, L, area, item);
@@ -319,47 +276,30 @@ prior_pair_kernel(const cbo_set_desc* __restrict__ sets, const __grid_constant__
             }
         }
     } else {
-        // =============================== 16 CONSUMER WARPS ===============================
-        int prev_CB = -1;
+        setmaxnreg_inc<kPairConsRegs>();
+        int prev_geom = -1;
 #pragma unroll 1
         for (int item = blockIdx.x; item < L.total_items; item += gridDim.x) {
-            int RB, CB;
-            {
-                const PairItem it = decode_pair_item(sets, L, area, item);
-                const int ra = it.pa - it.ca * it.CRa, rb = it.pb - it.cb * it.CRb;
-                RB = ((ra < it.CRa ? ra : it.CRa) + 7) >> 3, CB = ((rb < it.CRb ? rb : it.CRb) + 7) >> 3;
-            }
-            // The second-level slots are indexed by tile block (r * CB + c): when the tile geometry changes between two items
-            // of this CTA (chunked operands, sets with different grids) a block of the new item maps onto the slot another
-            // warp may still be reading for the old one.  The consumer warps (which walk the same item sequence) meet at a
-            // named barrier in that case; items of one geometry -- every item of the shipped configurations -- never do.
-            if (prev_CB >= 0 && prev_CB != CB) asm volatile("bar.sync 1, %0;" ::"n"(kPairNCons) : "memory");
-            prev_CB = CB;
-            // Shares of the 16 warps.  Why 16 warps: one warp issues a DMMA.8x8x4 at most every ~32 cycles (half the pipe's
-            // rate), so with 2 warps per scheduler the LARGEST share sets the pace (8 warps with 7x4 | 7x3 | 6x3 | 6x4 shares:
-            // 28 of 169 blocks -> 76 % of the pipe at best, and evening out the schedulers' sums did not help); with 4 warps
-            // per scheduler the pipe, not a warp, is the limit.
-            int nr, nc, row0, col0;
-            if (RB == 13 && CB == 13) {
-                // The shipped shape (100-point dimensions): 169 blocks in 16 rectangles of at most 12 blocks (48 accumulator
-                // registers): rows 0-3 x {0-2, 3-5, 6-8, 9-11}, the strip rows 0-6 x column 12, rows 4-6 x {0-3, 4-7, 8-11},
-                // rows 7-9 and 10-12 x {0-3, 4-6, 7-9, 10-12}; dealt so that the schedulers (warp & 3) carry 42 / 42 / 42 / 43.
-                //                          warp:  0   1   2   3   4   5   6   7   8   9  10  11  12  13  14  15
-                constexpr unsigned char kR0[16] = {0,  0,  0,  0,  4,  4,  4,  0,  7,  7,  7,  7, 10, 10, 10, 10};
-                constexpr unsigned char kNr[16] = {4,  4,  4,  4,  3,  3,  3,  7,  3,  3,  3,  3,  3,  3,  3,  3};
-                constexpr unsigned char kC0[16] = {0,  3,  6,  9,  0,  4,  8, 12,  4,  7, 10,  0,  4,  7, 10,  0};
-                constexpr unsigned char kNc[16] = {3,  3,  3,  3,  4,  4,  4,  1,  3,  3,  3,  4,  3,  3,  3,  4};
-                nr = kNr[warp], nc = kNc[warp], row0 = kR0[warp] * 8, col0 = kC0[warp] * 8;
-            } else {
-                // any other tile: 4 row groups x 4 column groups (sizes differ by at most one, the larger ones first), the 16
-                // rectangles dealt as a Latin square: warp w (scheduler q = w & 3, row group g = w >> 2) takes column group
-                // (q - g) & 3, so every scheduler gets one rectangle of every row group and of every column group
-                const int q = warp & 3, g = warp >> 2, cg = (q - g) & 3;
-                const int rbase = RB >> 2, rrem = RB & 3, cbase = CB >> 2, crem = CB & 3;
-                nr = rbase + (g < rrem ? 1 : 0), nc = cbase + (cg < crem ? 1 : 0);
-                row0 = (g * rbase + (g < rrem ? g : rrem)) * 8, col0 = (cg * cbase + (cg < crem ? cg : crem)) * 8;
-            }
-#define CBO_PC(A_, B_) pair_consume<A_, B_>(sets, L, area, item, smem, acc2, full, empty, stage, phase, lane, row0, col0, CB)
+            const PairItem it = decode_pair_item(sets, L, area, item);
+            // live 8 x 8 blocks of this tile, dealt to 2 x 4 warps: row halves (ceil | floor), column quarters with the
+            // larger ones first; the second row half takes the quarters in reverse so that warps w and w + 4 (same
+            // scheduler) pair a large share with a small one
+            const int ra = it.pa - it.ca * it.CRa, rb = it.pb - it.cb * it.CRb;
+            const int RB = ((ra < it.CRa ? ra : it.CRa) + 7) >> 3, CB = ((rb < it.CRb ? rb : it.CRb) + 7) >> 3;
+            // The second-level slots are indexed by tile block and the block -> warp map depends on (RB, CB): when the tile
+            // geometry changes between two items of this CTA (chunked operands, sets with different grids), a warp that is
+            // already in the new item could touch a slot a slower warp still owns under the old map.  The consumer warps
+            // (they walk the same item sequence) meet at a named barrier in that case; the shipped configurations (every
+            // tile 13 x 13) never do.
+            if (prev_geom >= 0 && prev_geom != RB * 16 + CB) asm volatile("bar.sync 1, %0;" ::"n"(kPairNCons) : "memory");
+            prev_geom = RB * 16 + CB;
+            const int wm = warp >> 2, wn = warp & 3;
+            const int rtop = (RB + 1) >> 1;
+            const int nr = wm == 0 ? rtop : RB - rtop, rblk0 = wm == 0 ? 0 : rtop;
+            const int gq = wm == 0 ? wn : 3 - wn, cbase = CB >> 2, crem = CB & 3;
+            const int nc = cbase + (gq < crem ? 1 : 0), cblk0 = gq * cbase + (gq < crem ? gq : crem);
+            const int row0 = rblk0 * 8, col0 = cblk0 * 8;
+#define CBO_PC(NR_, NC_) pair_consume<NR_, NC_>(it, smem, acc2, full, empty, stage, phase, lane, row0, col0, CB)
 #define CBO_PC_ROW(NR_)                                                        \
     switch (nc) {                                                              \
         case 1: CBO_PC(NR_, 1); break;                                         \
@@ -368,12 +308,15 @@ prior_pair_kernel(const cbo_set_desc* __restrict__ sets, const __grid_constant__
         default: CBO_PC(NR_, 4); break;                                        \
     }
             if (nr <= 0 || nc <= 0) CBO_PC(0, 0);
-            else if (nr == 7) CBO_PC(7, 1);
             else switch (nr) {
                 case 1: CBO_PC_ROW(1); break;
                 case 2: CBO_PC_ROW(2); break;
                 case 3: CBO_PC_ROW(3); break;
-                default: CBO_PC_ROW(4); break;
+                case 4: CBO_PC_ROW(4); break;
+                case 5: CBO_PC_ROW(5); break;
+                case 6: CBO_PC_ROW(6); break;
+                case 7: CBO_PC_ROW(7); break;
+                default: CBO_PC_ROW(8); break;
             }
 #undef CBO_PC_ROW
 #undef CBO_PC

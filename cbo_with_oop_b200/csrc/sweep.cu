@@ -109,8 +109,12 @@ __device__ __forceinline__ void posterior_sep(const SweepSmem& sm, int n, const 
 // NREG: register budget of the forward substitution, picked per LAUNCH from the largest n_int of the call (16 / 32 / 48
 // solution entries in registers; 0: any n, the vector lives in shared memory).  One instantiation per launch keeps the
 // small-n kernel (the reference's n = 10 .. ~50) at a register count that lets many CTAs share an SM.
-template <int NREG>
-__global__ void __launch_bounds__(kSweepThreads, NREG == 16 ? 5 : (NREG == 32 ? 3 : (NREG == 0 ? 5 : 2)))
+// SEP: the launch handles the sets whose posterior is evaluated through the separable k* tables (sweep_separable, not
+// posterior_cached); the SEP = false launch handles every other set.  A set's arithmetic therefore never depends on which
+// other sets share the call (ranks that hold different subsets must produce the same bits), and each instantiation
+// carries one path only (half the code, fewer live registers).
+template <int NREG, bool SEP>
+__global__ void __launch_bounds__(kSweepThreads, NREG == 16 ? 5 : (NREG == 0 ? 5 : 3))
 sweep_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, double best, double task_sign,
              cbo_set_best* __restrict__ tile_best) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -120,7 +124,8 @@ sweep_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, double best, d
     const int n = S.n_int, d = S.d, tid = threadIdx.x;
     const bool causal = S.causal != 0;
     const bool cached = S.posterior_cached != 0;   // mu / var of an earlier sweep are still valid: EI refresh only
-    const bool sep = NREG > 0 && !cached && sweep_separable(S);
+    if ((!cached && sweep_separable(S)) != SEP) return;       // the other launch's set
+    const bool sep = SEP;
     const int p_last = S.points ? 1 : S.p[d - 1];
 
     SweepSmem sm;
@@ -218,12 +223,8 @@ sweep_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, double best, d
             const double mg = causal ? S.m[loc] : 0.0;
             const double svg = causal ? sqrt(vg) : 0.0;
             double ss;
-            if constexpr (NREG > 0) {
-                if (sep) posterior_sep<NREG>(sm, n, eLast + jj, ldl, eLead + (int)(row - row_first), ldr, svg, mu, ss);
-                else posterior_at<NREG>(sm, n, d, x, svg, tid, mu, ss);
-            } else {
-                posterior_at<0>(sm, n, d, x, svg, tid, mu, ss);
-            }
+            if constexpr (SEP) posterior_sep<NREG>(sm, n, eLast + jj, ldl, eLead + (int)(row - row_first), ldr, svg, mu, ss);
+            else posterior_at<NREG>(sm, n, d, x, svg, tid, mu, ss);
             mu += mg;
             var = ((1.0 + vg) - ss) + 1e-10;
             if (S.mu) S.mu[loc] = mu;
@@ -348,6 +349,7 @@ int sweep_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_s
     CBO_REQUIRE(d_tile_best && d_set_best && d_result, "cbo_sweep: NULL output pointer");
     long long total = 0;
     int nmax = 1;
+    bool any_sep = false, any_gen = false;   // sets for the separable-table launch / for the general launch
     size_t tab_doubles = 0;      // the two k* tables of the separable path, or the generic path's [n][threads] workspace
     for (int s = 0; s < num_sets; ++s) {
         const cbo_set_desc& S = h_sets[s];
@@ -359,18 +361,37 @@ int sweep_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_s
         total += host_items(S, kItemsSweep);
         if (S.n_int > nmax) nmax = S.n_int;
         size_t t = 0;
-        if (!S.posterior_cached && sweep_separable(S)) t = (size_t)S.n_int * ((S.p[S.d - 1] | 1) + (sweep_lead_rows(S) | 1));
+        if (S.g_count > 0) {
+            if (!S.posterior_cached && sweep_separable(S)) {
+                t = (size_t)S.n_int * ((S.p[S.d - 1] | 1) + (sweep_lead_rows(S) | 1));
+                any_sep = true;
+            } else {
+                any_gen = true;
+            }
+        }
         if (t > tab_doubles) tab_doubles = t;
     }
     CBO_REQUIRE(total < 2147483647LL, "cbo_sweep: too many work items");
     if (total > 0) {
-        if (nmax > 48) tab_doubles = (size_t)nmax * kSweepThreads;     // generic path: [n][threads] solution workspace, no tables
-        const size_t smem = ((size_t)nmax * (nmax + 1) / 2 + 2 * (size_t)nmax + (size_t)nmax * CBO_MAX_D + tab_doubles) * sizeof(double);
-        auto kern = nmax <= 16 ? sweep_kernel<16> : (nmax <= 32 ? sweep_kernel<32> : (nmax <= 48 ? sweep_kernel<48> : sweep_kernel<0>));
-        if (smem > 48 * 1024) CBO_CUDA(allow_dynamic_smem(kern, smem));
-        kern<<<(unsigned)total, kSweepThreads, smem, st>>>(d_sets, num_sets, best, (double)task_sign, d_tile_best);
-        note_launch();
-        CBO_CUDA(cudaGetLastError());
+        // sets with n_int > 48 are not separable (sweep_separable), so the table launch never needs the generic workspace
+        const size_t base = ((size_t)nmax * (nmax + 1) / 2 + 2 * (size_t)nmax + (size_t)nmax * CBO_MAX_D) * sizeof(double);
+        if (any_sep) {
+            const size_t smem = base + tab_doubles * sizeof(double);
+            auto kern = nmax <= 16 ? sweep_kernel<16, true> : (nmax <= 32 ? sweep_kernel<32, true> : sweep_kernel<48, true>);
+            if (smem > 48 * 1024) CBO_CUDA(allow_dynamic_smem(kern, smem));
+            kern<<<(unsigned)total, kSweepThreads, smem, st>>>(d_sets, num_sets, best, (double)task_sign, d_tile_best);
+            note_launch();
+            CBO_CUDA(cudaGetLastError());
+        }
+        if (any_gen) {
+            const size_t smem = base + (nmax > 48 ? (size_t)nmax * kSweepThreads * sizeof(double) : 0);
+            auto kern = nmax <= 16 ? sweep_kernel<16, false> : (nmax <= 32 ? sweep_kernel<32, false> :
+                        (nmax <= 48 ? sweep_kernel<48, false> : sweep_kernel<0, false>));
+            if (smem > 48 * 1024) CBO_CUDA(allow_dynamic_smem(kern, smem));
+            kern<<<(unsigned)total, kSweepThreads, smem, st>>>(d_sets, num_sets, best, (double)task_sign, d_tile_best);
+            note_launch();
+            CBO_CUDA(cudaGetLastError());
+        }
     }
     set_reduce_kernel<<<num_sets, 256, 0, st>>>(d_sets, num_sets, d_tile_best, d_set_best);
     note_launch();

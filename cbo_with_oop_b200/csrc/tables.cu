@@ -87,6 +87,22 @@ tables_batched_kernel(const cbo_set_desc* __restrict__ sets) {
     }
 }
 
+// The interventional-row table of ONE set, rows [int_row_begin, n_int) only (a post-intervention trial appends one row; the
+// grid tables do not depend on x_int).
+int int_rows_table_impl(const cbo_set_desc& S, cudaStream_t st) {
+    if (!computes_prior(S) || S.int_row_begin >= S.n_int) return 0;
+    CBO_REQUIRE(S.u_int && S.x_int && S.x_obs_int, "cbo_refresh_trial: NULL u_int/x_int/x_obs_int pointer");
+    const int r0 = S.int_row_begin, rows = S.n_int - r0;
+    const double il[CBO_MAX_D] = {1.0 / S.ls_int[0], S.d > 1 ? 1.0 / S.ls_int[1] : 0.0, S.d > 2 ? 1.0 / S.ls_int[2] : 0.0,
+                                  S.d > 3 ? 1.0 / S.ls_int[3] : 0.0};
+    points_table_kernel<<<dim3((S.n_obs_pad + 255) / 256, (unsigned)(rows < 1024 ? rows : 1024)), 256, 0, st>>>(
+        S.x_int + (size_t)r0 * S.d, rows, S.d, S.x_obs_int, S.n_obs, S.n_obs_pad, il[0], il[1], il[2], il[3],
+        S.u_int + (size_t)r0 * S.n_obs_pad);
+    note_launch();
+    CBO_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int build_tables_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_sets, cudaStream_t st) {
     bool batched = d_sets != nullptr && num_sets > 1 && num_sets * (CBO_MAX_D + 1) <= 65535;
     if (batched) {

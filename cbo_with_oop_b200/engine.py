@@ -214,12 +214,18 @@ class SweepEngine:
         ws = self.lib.cbo_prior_workspace_bytes(self.h_sets, A, self.num_sms) if A else 0
         self.prior_ws = torch.empty((max(ws, 256),), dtype=torch.uint8, device=self.device)
         self.tile_best = torch.empty((max(n_items, 1) * C.sizeof(SetBest),), dtype=torch.uint8, device=self.device)
-        self.local_best = torch.empty((max(A, 1) * C.sizeof(SetBest),), dtype=torch.uint8, device=self.device)
         S = len(self.problems)
-        # [cbo_sweep_result | S x cbo_set_best]: the step's whole result, read back with ONE device -> host copy
+        # [cbo_sweep_result | S x cbo_set_best]: the step's whole result, read back with ONE device -> host copy into pinned
+        # memory (an event, not a blocking .cpu()).  On a single rank that touches every set the sweep's own per-set
+        # reduction writes straight into the global table (local ids == global ids): no scatter, no second combine.
         self.out_buf = torch.empty((C.sizeof(SweepResult) + S * C.sizeof(SetBest),), dtype=torch.uint8, device=self.device)
+        self.out_host = torch.empty((self.out_buf.numel(),), dtype=torch.uint8).pin_memory()
+        self._out_event = torch.cuda.Event()
         self.result = self.out_buf[:C.sizeof(SweepResult)]
         self.global_best = self.out_buf[C.sizeof(SweepResult):]
+        self._direct = self.world == 1 and self.active == list(range(S))
+        self.local_best = self.global_best if self._direct else \
+            torch.empty((max(A, 1) * C.sizeof(SetBest),), dtype=torch.uint8, device=self.device)
         self.gathered = torch.empty((self.world * S * C.sizeof(SetBest),), dtype=torch.uint8, device=self.device)
         empty = (SetBest * S)()
         for s in range(S):
@@ -452,21 +458,27 @@ class SweepEngine:
         the device with the same deterministic rule on every rank, and read the 24-byte result back."""
         S, sb = len(self.problems), C.sizeof(SetBest)
         gb = self.global_best
-        gb.copy_(self._empty_best)
-        gv, lv = gb.view(S, sb), self.local_best.view(-1, sb)
-        if self.active:
-            idx = torch.as_tensor(self.active, device=self.device, dtype=torch.long)
-            gv.index_copy_(0, idx, lv[:len(self.active)])
-        if self.world > 1:
-            from .dist import gather_set_bests
-            gather_set_bests(gb, self.gathered, self.world, self.group)
-            src, nr = self.gathered, self.world
-        else:   # combine_kernel's input and output must not alias (both are __restrict__): stage the table like a 1-rank gather
-            self.gathered[:gb.numel()].copy_(gb)
-            src, nr = self.gathered, 1
-        _lib.check(self.lib.cbo_argmax_combine(C.c_void_p(src.data_ptr()), nr, S, C.c_void_p(gb.data_ptr()),
-                                               C.c_void_p(self.result.data_ptr()), self._stream()), "cbo_argmax_combine")
-        out_h = self.out_buf.cpu().numpy().tobytes()     # ONE device -> host read of the step's result (synchronises)
+        if not self._direct:
+            gb.copy_(self._empty_best)
+            gv, lv = gb.view(S, sb), self.local_best.view(-1, sb)
+            if self.active:
+                if not hasattr(self, "_active_idx"):
+                    self._active_idx = torch.as_tensor(self.active, device=self.device, dtype=torch.long)
+                gv.index_copy_(0, self._active_idx, lv[:len(self.active)])
+            if self.world > 1:
+                from .dist import gather_set_bests
+                gather_set_bests(gb, self.gathered, self.world, self.group)
+                src, nr = self.gathered, self.world
+            else:   # combine_kernel's input and output must not alias (both are __restrict__): stage the table like a 1-rank gather
+                self.gathered[:gb.numel()].copy_(gb)
+                src, nr = self.gathered, 1
+            _lib.check(self.lib.cbo_argmax_combine(C.c_void_p(src.data_ptr()), nr, S, C.c_void_p(gb.data_ptr()),
+                                                   C.c_void_p(self.result.data_ptr()), self._stream()), "cbo_argmax_combine")
+        # ONE device -> host read of the step's result, into pinned memory; wait on its event only
+        self.out_host.copy_(self.out_buf, non_blocking=True)
+        self._out_event.record(torch.cuda.current_stream(self.device))
+        self._out_event.synchronize()
+        out_h = self.out_host.numpy().tobytes()
         res_h, best_h = out_h[:C.sizeof(SweepResult)], out_h[C.sizeof(SweepResult):]
         r = SweepResult.from_buffer_copy(res_h)
         bests = (SetBest * S).from_buffer_copy(best_h)
@@ -524,10 +536,31 @@ class SweepEngine:
         their interventional table, prior at x_int and posterior refreshed
         (CBO.update_gaussian_process_of_last_intervention, CBO.py:224-235), then EI everywhere."""
         ev: list = []
+        if task not in ("min", "max"):
+            raise ValueError("task must be 'min' or 'max'")
         # sets that are not refitted keep their posterior: their share of the sweep is a 16 B/candidate EI refresh.
         # Both flags go into the descriptors before the first kernel: one upload for the whole trial.
         self._set_row_begin({g: self._row_begin.get(g, 0) for g in refit if g in self._prior_rows_valid})
         self._mark_cached(self._posterior_valid - set(refit))
+        refit_local = [self.local_of[g] for g in refit if g in self.local_of]
+        if not self.timing and len(refit_local) <= 1 and self.active:
+            # the whole trial in one library call (cbo_refresh_trial): descriptor upload, the appended rows' table and prior,
+            # the refit, the sweep and its reductions -- six launches, no Python between them
+            li = refit_local[0] if refit_local else -1
+            _lib.check(self.lib.cbo_refresh_trial(self.h_sets, C.c_void_p(self.d_sets.data_ptr()), len(self.active), li, float(best),
+                                                  1 if task == "min" else -1, C.c_void_p(self.prior_ws.data_ptr()),
+                                                  self.prior_ws.numel(), C.c_void_p(self.tile_best.data_ptr()),
+                                                  C.c_void_p(self.local_best.data_ptr()), C.c_void_p(self.result.data_ptr()),
+                                                  self._stream()), "cbo_refresh_trial")
+            self._descs_dirty = False
+            for g in refit:
+                if g in self.local_of and self.problems[g].computes_prior:
+                    self._prior_rows_valid.add(g)
+                    self._row_begin.pop(g, None)
+            self._set_row_begin({})
+            self._mark_cached(set())
+            self._posterior_valid = set(self.active)
+            return self._finish(ev)
         for g in refit:
             if g not in self.local_of:
                 continue

@@ -213,6 +213,16 @@ CBO_API int cbo_sweep(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, in
               int task_sign, cbo_set_best* d_tile_best, cbo_set_best* d_set_best,
               cbo_sweep_result* d_result, void* stream);
 
+/* A whole post-intervention trial in ONE call (CBO.update_gaussian_process_of_last_intervention + compute_best_acquisition_values,
+ * CBO.py:224-260, after Monitor.add_intervention_data :148-160 appended one row to set `refit_set`): uploads the descriptor
+ * array (it carries the trial's n_int / int_row_begin / posterior_cached flags), evaluates the interventional-row table and
+ * the prior of the rows [int_row_begin, n_int) of that set only, refits it, and sweeps every set -- sets marked
+ * posterior_cached only refresh EI from their mu / var arrays (16 B per candidate).  refit_set = -1: sweep only.
+ * Six launches and one 480 B x num_sets copy; the per-stage entry points above remain for callers that time the stages. */
+CBO_API int cbo_refresh_trial(const cbo_set_desc* h_sets, cbo_set_desc* d_sets, int num_sets, int refit_set, double best,
+                              int task_sign, void* d_workspace, size_t workspace_bytes, cbo_set_best* d_tile_best,
+                              cbo_set_best* d_set_best, cbo_sweep_result* d_result, void* stream);
+
 /* K4 (multi-GPU). Combine `num_ranks` gathered per-set bests (rank-major: [rank][set]) into the global
  * per-set bests and the global result with the same rule on every rank.  Runs on the device so the
  * all-gathered buffer never leaves it. */

@@ -1,7 +1,7 @@
 """Run the REFERENCE's own modules (unmodified, imported from /root/reference) on the inputs frozen in
 tests/golden/golden_<config>.npz and store what they return -> tests/golden/reference_run_<config>.npz.
 
-    python tests/golden/make_reference_golden.py [toy complete]        (build container only: needs /root/reference)
+    python tests/golden/make_reference_golden.py [toy complete simplified_coral]        (build container only: needs /root/reference)
 
 The reference's third-party dependencies (GPy, emukit, paramz) are absent from this image; tests/golden/gpy_standin/
 supplies the API surface the reference imports (see its README for exactly what is and is not pinned by this).
@@ -68,7 +68,11 @@ def do_closure(do, measurements, gp, input_vars, intervention_vars, index, memo)
     return f
 
 
-def run(config, max_keep):
+def run(config, max_keep, max_full=20000, sample=4096):
+    """Sets with at most `max_full` candidates are evaluated on the whole grid.  Larger ones (the 1e6-candidate 3-D sets of
+    the coral family: about 1 ms per candidate through the reference's per-candidate gp.predict) are evaluated on a seeded
+    sample of `sample` candidates plus the 3^d neighbourhood of the oracle's argmax (golden_<config>.npz), flagged
+    `sampled`: their `idx` / `val` are the maximum over that subset and `n_nan` counts the subset only."""
     z = np.load(os.path.join(HERE, f"golden_{config}.npz"))
     S = int(z["num_sets"])
     task = str(z["task"])
@@ -102,7 +106,20 @@ def run(config, max_keep):
         ei_acq = CausalExpectedImprovement(best, task, model)
         acquisition = ei_acq / Cost(costs, iv)
         tables = [np.linspace(lo, hi, int(p)) for lo, hi, p in z[k + "grid_lo_hi_p"]]
-        Xg = np.stack([g.reshape(-1) for g in np.meshgrid(*tables, indexing="ij")], axis=1)
+        shape = [len(t) for t in tables]
+        G_full = int(np.prod(shape))
+        sampled = G_full > max_full
+        if sampled:
+            rng = np.random.default_rng(2000 + s)
+            centre = np.unravel_index(int(z[k + "idx"]), shape)
+            nb = np.stack(np.meshgrid(*[np.clip(np.arange(c_ - 1, c_ + 2), 0, p_ - 1) for c_, p_ in zip(centre, shape)],
+                                      indexing="ij"), axis=-1).reshape(-1, len(shape))
+            flat = np.unique(np.concatenate([rng.choice(G_full, size=sample, replace=False),
+                                             np.ravel_multi_index(nb.T, shape)]))
+        else:
+            flat = np.arange(G_full)
+        ii = np.unravel_index(flat, shape)
+        Xg = np.stack([tables[a][ii[a]] for a in range(len(shape))], axis=1)
         G = Xg.shape[0]
         acq = np.empty(G)
         mu, var, ei, mg, vg = (np.empty(G) for _ in range(5))
@@ -116,9 +133,10 @@ def run(config, max_keep):
         nan = np.isnan(acq)
         idx = int(np.argmax(np.where(nan, -np.inf, acq)))
         ys.append(np.array([[acq[idx]]]))
-        keep = np.arange(0, G, max(1, -(-G // max_keep)))
+        keep = np.arange(G) if sampled else np.arange(0, G, max(1, -(-G // max_keep)))
+        pack[k + "sampled"] = np.array(int(sampled))
         post = model.model.posterior
-        pack.update({k + "keep": keep, k + "idx": np.array(idx), k + "val": np.array(acq[idx]), k + "x": Xg[idx],
+        pack.update({k + "keep": flat[keep], k + "idx": np.array(int(flat[idx])), k + "val": np.array(acq[idx]), k + "x": Xg[idx],
                      k + "n_nan": np.array(int(nan.sum())), k + "tries": np.array(int(post.jitter_tries)),
                      k + "mI": mean_fn(XI)[:, 0], k + "vI": var_fn(XI)[:, 0], k + "L": post.woodbury_chol,
                      k + "alpha": post.woodbury_vector[:, 0], k + "name": np.array(names[s])})
@@ -126,7 +144,7 @@ def run(config, max_keep):
             pack[k + nm] = arr[keep]
         srt = np.sort(acq[~nan])
         pack[k + "top2_gap"] = np.array((srt[-1] - srt[-2]) / abs(srt[-1]) if len(srt) > 1 and srt[-1] != 0 else np.inf)
-        print(f"  {config} set {s} {names[s]:3s} N={N} D={x.shape[1]} G={G} idx={idx} val={acq[idx]:.6e} "
+        print(f"  {config} set {s} {names[s]:3s} N={N} D={x.shape[1]} G={G}{' (sampled)' if sampled else ''} idx={int(flat[idx])} val={acq[idx]:.6e} "
               f"tries={post.jitter_tries} nan={int(nan.sum())}", flush=True)
     agent = types.SimpleNamespace(monitor=types.SimpleNamespace(last_intervention=None),
                                   exploration_set=[set_variables(n, len(n)) for n in names])
@@ -144,3 +162,5 @@ if __name__ == "__main__":
         run("toy", 4096)
     if "complete" in which:
         run("complete", 1024)
+    if "simplified_coral" in which:      # 25 sets: 1-D and 2-D sets in full, 3-D sets sampled (about ten minutes)
+        run("simplified_coral", 1024)

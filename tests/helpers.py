@@ -82,11 +82,15 @@ BACKWARD_TOL = 1e-12      # n * eps-level residuals of the Cholesky factor and o
 MODERATE_COND = 1e6       # below this the forward errors of L and alpha must also meet RTOL
 
 
-def sweep_errors(got, exp, k=""):
+def sweep_errors(got, exp, k="", ei_scale_floor=0.0):
     """Errors of one exploration set's sweep arrays under the parity rule of DESIGN.md §2.
-    got / exp: mappings with mI, vI, mg, vg, mu, var, ei, acq (got at the same candidates as exp); exp keys carry prefix k."""
+    got / exp: mappings with mI, vI, mg, vg, mu, var, ei, acq (got at the same candidates as exp); exp keys carry prefix k.
+    ei_scale_floor: lower bound of the scale EI / acquisition errors are measured on.  A set whose whole grid lies 17 sigma
+    from the incumbent has EI ~ 1e-70 everywhere; there d(EI)/EI ~ u du, so the 1e-9 that GPy's expanded distances lose at
+    coordinates ~2400 is a 1e-6 relative change of a number that cannot influence the trial (the winning set's
+    acquisition is ~30).  Callers comparing against the reference's own run pass 1e-6 x the trial's best acquisition."""
     kd = 1.0 + exp[k + "vg"]
-    ei_scale = max(np.nanmax(np.abs(exp[k + "ei"])), 1e-300)
+    ei_scale = max(np.nanmax(np.abs(exp[k + "ei"])), 1e-300, ei_scale_floor)
     return {
         "m_int": rel_err(got["mI"], exp[k + "mI"], 1e-6).max(),
         "v_int": rel_err(got["vI"], exp[k + "vI"], 1e-6).max(),
@@ -99,3 +103,39 @@ def sweep_errors(got, exp, k=""):
         "ei": np.nanmax(rel_err(got["ei"], exp[k + "ei"], 1e-6 * ei_scale)),
         "acq": np.nanmax(rel_err(got["acq"], exp[k + "acq"], 1e-6 * ei_scale)),
     }
+
+
+def oracle_at_reference_points(z, r, s, best, form, val_scale):
+    """The oracle's sweep arrays of set s of a golden fixture `z`, evaluated at the candidates a reference run `r` kept, with
+    the per-set GP's distances in `form` ('diff': coordinate differences, what the CUDA path uses; 'expanded': GPy's
+    |x|^2 + |y|^2 - 2 x.y, what the reference executes).  Returns (arrays, errors against r under the parity rule)."""
+    from cbo_with_oop_b200.obs_gp import fit_state
+    k = f"set{s}_"
+    X = np.hstack([z[k + "x_obs_int"], z[k + "x_obs_cond"]])
+    d = z[k + "x_obs_int"].shape[1]
+    ls = np.concatenate([z[k + "ls_int"], z[k + "ls_cond"]])
+    s2 = float(z[k + "s2"])
+    grid = [np.linspace(lo, hi, int(p)) for lo, hi, p in z[k + "grid_lo_hi_p"]]
+    kyinv = z[k + "kyinv"] if k + "kyinv" in z else fit_state(X, z[k + "y_obs"], s2, ls, 1e-2)[1]
+    gp = dict(X=X, variance=s2, lengthscale=ls, noise=1e-2, alpha=z[k + "alpha_obs"], Kyinv=kyinv, form="diff")
+    cols = list(range(d))
+    f = O.prior_factors(gp, X, cols)
+    mI, vI = O.do_prior_factorised(gp, f, cols, z[k + "x_int"], precise=True)
+    post = O.posterior_fit(z[k + "x_int"], z[k + "y_int"], mI, vI, form=form)
+    keep = r[k + "keep"]
+    ii = np.unravel_index(keep, [len(t) for t in grid])
+    Xg = np.stack([grid[a][ii[a]] for a in range(d)], axis=1)
+    mg, vg = O.do_prior_factorised(gp, f, cols, Xg, precise=True)
+    mu, var = O.posterior_predict(post, Xg, mg, vg)
+    ei = O.expected_improvement(mu, var, best, "min")
+    got = {"mI": mI, "vI": vI, "mg": mg, "vg": vg, "mu": mu, "var": var, "ei": ei, "acq": ei / float(z[k + "cost_fix"]),
+           "tries": post["tries"]}
+    return got, sweep_errors(got, r, k, ei_scale_floor=1e-6 * val_scale)
+
+
+def form_distance(a, b, k, val_scale):
+    """Distance between two evaluations (dicts as returned by oracle_at_reference_points) of the same set, measured the way
+    sweep_errors measures errors: the size of the reference's own distance-rounding noise when a and b are the oracle with
+    coordinate differences and with GPy's expanded form."""
+    names = ("mI", "vI", "mg", "vg", "mu", "var", "ei", "acq")
+    return {n: float(e) for n, e in sweep_errors(a, {k + n: b[n] for n in names}, k, ei_scale_floor=1e-6 * val_scale).items()}
