@@ -1,0 +1,31 @@
+"""One post-observation trial followed by a few post-intervention trials on a config-5-shaped set (development aid for
+profiling the appended-row path: prior_rows_kernel<4>, posterior_fit_kernel, sweep_kernel with one cached set).
+python tools/refresh_probe.py [--n-obs 10000] [--p 32 32 32]"""
+import argparse, json, os, sys
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+ap = argparse.ArgumentParser()
+ap.add_argument("--n-obs", type=int, default=10000)
+ap.add_argument("--p", type=int, nargs="+", default=[32, 32, 32])
+ap.add_argument("--trials", type=int, default=4)
+args = ap.parse_args()
+import numpy as np, torch
+from cbo_with_oop_b200.engine import SweepEngine
+from cbo_with_oop_b200.synthetic import best_of, scaled_set
+probs = []
+for i in range(2):
+    pr = scaled_set(i, n_obs=args.n_obs, p=max(args.p), d=len(args.p), c=3, n_int=32, device_fit=True)
+    pr.grid = [np.linspace(-2.0, 2.0, pk) for pk in args.p]
+    probs.append(pr)
+eng = SweepEngine(probs)
+best = best_of(probs)
+eng.sweep(best, "min")
+rng = np.random.default_rng(0)
+x, y = probs[0].x_int.copy(), probs[0].y_int.copy()
+ms = []
+for t in range(args.trials):
+    x = np.vstack([x, rng.uniform(-2, 2, (1, len(args.p)))]); y = np.append(y, 0.0)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); eng.set_interventional(0, x, y); out = eng.refresh(best, "min", refit=[0]); e1.record(); torch.cuda.synchronize()
+    ms.append(e0.elapsed_time(e1))
+print(json.dumps({"n_obs": args.n_obs, "p": args.p, "ms_per_post_intervention_trial": ms, "selected": [out.set, out.index]}))
