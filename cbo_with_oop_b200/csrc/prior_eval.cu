@@ -514,7 +514,9 @@ prior_eval_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, PriorSpli
                 // launch with more than one column block; 0 = regular tiling throughout.  CTA-uniform: every consumer
                 // warp of a full tile runs the LIVE == MA instantiation.
                 const int lc = S.n_obs - (it.nJ - 1) * BN;
-                const int ragged_cols = (!SPLIT && nlive == BM && it.nJ > 1 && lc <= 64) ? lc : 0;
+                // (the item must own that block: when the column blocks are dealt to several items per tile -- nsplit > 1, a
+                // grid with too few tiles for segments -- most items do not, and the producer streams nothing for it)
+                const int ragged_cols = (!SPLIT && nlive == BM && it.nJ > 1 && lc <= 64 && it.mine(it.nJ - 1)) ? lc : 0;
 #define CBO_CONSUME(LIVE) consume_item<Cfg, LIVE, SPLIT>(it, sA, sB, sRed, full, empty, stage, phase, scratch, S.w, warp, lane, ragged_cols)
                 if (need >= 7) CBO_CONSUME(8);
                 else if (need == 6) CBO_CONSUME(6);

@@ -48,10 +48,17 @@ __device__ __forceinline__ void posterior_at(const SweepSmem& sm, int n, int d, 
                 const double ks = exp(-0.5 * r2) + sm.sv[i] * svg;
                 mu = fma(ks, sm.al[i], mu);
                 const double* __restrict__ Li = sm.Lp + i * (i + 1) / 2;
-                double a = ks;
+                // four interleaved partial sums: the row's dot product is a dependent FMA chain, and with 3-5 CTAs per SM
+                // the FP64 latency, not the pipe, set the pace (1e3 dependent FMAs per candidate at n = 45)
+                double a0 = ks, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-                for (int j = 0; j < i; ++j) a = fma(-Li[j], t[j], a);
-                t[i] = a * Li[i];     // Li[i] = 1 / L[i][i]: one division per set entry at staging, not one per candidate and row
+                for (int j = 0; j < i; ++j) {
+                    if ((j & 3) == 0) a0 = fma(-Li[j], t[j], a0);
+                    else if ((j & 3) == 1) a1 = fma(-Li[j], t[j], a1);
+                    else if ((j & 3) == 2) a2 = fma(-Li[j], t[j], a2);
+                    else a3 = fma(-Li[j], t[j], a3);
+                }
+                t[i] = ((a0 + a1) + (a2 + a3)) * Li[i];     // Li[i] = 1 / L[i][i]: staged once per item, no division per candidate and row
                 ss = fma(t[i], t[i], ss);
             }
         }
@@ -97,10 +104,15 @@ __device__ __forceinline__ void posterior_sep(const SweepSmem& sm, int n, const 
             const double ks = fma(eLead[i * ldr], eLast[i * ldl], sm.sv[i] * svg);
             mu = fma(ks, sm.al[i], mu);
             const double* __restrict__ Li = sm.Lp + i * (i + 1) / 2;
-            double a = ks;
+            double a0 = ks, a1 = 0.0, a2 = 0.0, a3 = 0.0;      // (four interleaved partial sums, as in posterior_at)
 #pragma unroll
-            for (int j = 0; j < i; ++j) a = fma(-Li[j], t[j], a);
-            t[i] = a * Li[i];
+            for (int j = 0; j < i; ++j) {
+                if ((j & 3) == 0) a0 = fma(-Li[j], t[j], a0);
+                else if ((j & 3) == 1) a1 = fma(-Li[j], t[j], a1);
+                else if ((j & 3) == 2) a2 = fma(-Li[j], t[j], a2);
+                else a3 = fma(-Li[j], t[j], a3);
+            }
+            t[i] = ((a0 + a1) + (a2 + a3)) * Li[i];
             ss = fma(t[i], t[i], ss);
         }
     }

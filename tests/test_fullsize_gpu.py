@@ -82,3 +82,24 @@ def test_config5_one_set_full_size(cuda_engine_ready):
         np.testing.assert_array_equal(e.fetch("acq", 0), acq[gb:gb + gc])
         del e
         torch.cuda.empty_cache()
+
+
+def test_small_tensor_grid_at_full_n_obs(cuda_engine_ready):
+    """A 2048-candidate tensor grid at N = 10^4 (16 full tiles: too few for M's triangle to be cut into segments, so the column
+    blocks are dealt to several items per tile) with a ragged last column block (10^4 = 78 * 128 + 16): the item that does NOT
+    own the last block must not wait for it (a round-1 deadlock: the kernel trapped).  Checked against the explicit-point path."""
+    import torch
+    from cbo_with_oop_b200.engine import SweepEngine
+    from cbo_with_oop_b200.synthetic import scaled_set
+    pr = scaled_set(3, n_obs=10_000, p=16, d=3, c=3, n_int=32, device_fit=True)
+    pr.grid = [np.linspace(-2.0, 2.0, pk) for pk in (8, 16, 16)]
+    eng = SweepEngine([pr])
+    out = eng.sweep(float(np.min(pr.y_int)), "min")
+    torch.cuda.synchronize()
+    m, v = eng.fetch("m", 0), eng.fetch("v", 0)
+    assert np.all(np.isfinite(m)) and np.all(np.isfinite(v)) and 0 <= out.index < 2048
+    flat = np.arange(0, 2048, 7)
+    ii = np.unravel_index(flat, (8, 16, 16))
+    X = np.stack([pr.grid[k][ii[k]] for k in range(3)], axis=1)
+    pts = eng.evaluate_points(0, X, stages="prior")
+    assert rel_err(m[flat], pts["m"], 1e-6).max() <= 1e-9 and rel_err(v[flat], pts["v"], 1e-6).max() <= 1e-9
