@@ -16,11 +16,12 @@ from oracle import cbo_oracle as O
 pytestmark = pytest.mark.gpu
 
 
-def test_config5_one_set_full_size(cuda_engine_ready):
+@pytest.mark.parametrize("set_index,n_sample", [(3, 192), (11, 512)])
+def test_config5_one_set_full_size(cuda_engine_ready, set_index, n_sample):
     import torch
     from cbo_with_oop_b200.engine import SweepEngine
     from cbo_with_oop_b200.synthetic import scaled_set
-    pr = scaled_set(3, n_obs=10_000, p=100, d=3, c=3, n_int=32, device="cuda:0")
+    pr = scaled_set(set_index, n_obs=10_000, p=100, d=3, c=3, n_int=32, device="cuda:0")
     best = float(pr.y_int.min())
     eng = SweepEngine([pr], keep=("mu", "var", "ei", "acq"))
     out = eng.sweep(best, "min")
@@ -44,7 +45,7 @@ def test_config5_one_set_full_size(cuda_engine_ready):
 
     # ---- oracle parity on a seeded sample of candidates (plus the selected one)
     rng = np.random.default_rng(0)
-    idx = np.unique(np.concatenate([rng.choice(G, 192, replace=False), flat[:8], [out.index]]))
+    idx = np.unique(np.concatenate([rng.choice(G, n_sample, replace=False), flat[:8], [out.index]]))
     Xs = np.stack([pr.grid[k][np.unravel_index(idx, shape)[k]] for k in range(3)], 1)
     X = np.hstack([pr.x_obs_int, pr.x_obs_cond])
     gp = dict(X=X, variance=pr.s2, lengthscale=np.concatenate([pr.ls_int, pr.ls_cond]), noise=pr.noise, alpha=pr.alpha_obs,

@@ -33,14 +33,14 @@ rows = list(csv.reader(io.StringIO(src)))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
 h, data = rows[hi], rows[hi + 1:]
 isrc, iss, iex = h.index("Source"), h.index("Warp Stall Sampling (All Samples)"), h.index("Instructions Executed")
-iwx = h.index("L1 Wavefronts Shared Excessive")
+iwx = h.index("L1 Wavefronts Shared Excessive") if "L1 Wavefronts Shared Excessive" in h else None
 tot = sum(int(r[iss] or 0) for r in data) or 1
 hot = sorted(((int(r[iss] or 0), n, r) for n, r in enumerate(data)), reverse=True)[:top]
 out["hot_sass"] = []
 print(f"total samples {tot}; hottest SASS lines:")
 for s_, n, r in sorted(hot, key=lambda t: t[1]):
-    line = {"line": n, "sass": r[isrc][:80], "samples_pct": round(100 * s_ / tot, 2), "executed": r[iex], "smem_excess_wavefronts": r[iwx]}
+    line = {"line": n, "sass": r[isrc][:80], "samples_pct": round(100 * s_ / tot, 2), "executed": r[iex], "smem_excess_wavefronts": (r[iwx] if iwx is not None else None)}
     out["hot_sass"].append(line)
-    print(f"{n:5d} {r[isrc][:72]:72s} {100*s_/tot:6.2f}% exec={r[iex]} wfx={r[iwx]}")
+    print(f"{n:5d} {r[isrc][:72]:72s} {100*s_/tot:6.2f}% exec={r[iex]} wfx={r[iwx] if iwx is not None else None}")
 if "--json" in sys.argv:
     json.dump(out, open(sys.argv[sys.argv.index("--json") + 1], "w"), indent=1)
