@@ -23,7 +23,9 @@
 //   alpha     z = Wt^T y (partial sums over row chunks, added in order), alpha = Wt z     (two HBM-bound passes over Wt)
 // A non-positive pivot is reported through `info` (1 + the panel index); the caller retries with GPy's jitter rule.
 // Launch-latency bound for small N (3 launches per panel); at N = 1e4 the tile products dominate.
-#include "dmma_tile.cuh"
+#include <stdlib.h>
+
+#include "dmma_tma_tile.cuh"
 
 namespace cbo {
 
@@ -62,38 +64,155 @@ gram_kernel(ObsX X, int n, int npad, double s2, double diag_add, double* __restr
     }
 }
 
-// Cholesky + in-place triangular inverse of diagonal block p.  One CTA.
+// ---- diagonal block: Cholesky + triangular inverse of one 128 x 128 block, one CTA ---------------------------------------
+// Blocked over 32 x 32 sub-blocks so that the serial part runs inside ONE warp on registers and shuffles (no CTA barrier
+// per column: the column-by-column version spent 42 % of its 257 us in barrier stalls, profiles/r02_k5_potrf_diag_*):
+//   phase A, for b = 0..3:   warp 0   Cholesky of sub-block (b, b): lane i owns row i, pivots and columns travel by shuffle
+//                            warp 4   inverse of that sub-block (lane c owns column c of L_bb^-1: forward substitution)
+//                            warps 1-3  rows below: X L_bb^T = A_rb by forward substitution, one thread per row
+//                            all      trailing update B[i][k] -= sum_m X[i][m] X[k][m]   (register-tiled, 16 x 16 threads)
+//   phase B:  W = L^-1 by block recursion  W21 = -W22 L21 W11  on 32- and then 64-wide halves (four small products).
+constexpr int kSB = 32;
+constexpr int kSubLd = kSB + 1;
+constexpr int kHalfLd = 2 * kSB + 1;
+constexpr size_t kDiagSmemDoubles = (size_t)kFB * kDiagLd + 4 * kSB * kSubLd + 2 * kSB * kHalfLd + kSB;
+
+// acc[a][c] = sum_{k < K} A[(ty + 16 a)][k] * Bm[k][tx + 16 c]   (row-major shared-memory operands, 16 x 16 threads)
+template <int MI, int NJ>
+__device__ __forceinline__ void smem_product(double (&acc)[MI][NJ], const double* A, int lda, const double* Bm, int ldb, int K,
+                                             int ty, int tx) {
+#pragma unroll
+    for (int a = 0; a < MI; ++a)
+#pragma unroll
+        for (int c = 0; c < NJ; ++c) acc[a][c] = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+        double av[MI], bv[NJ];
+#pragma unroll
+        for (int a = 0; a < MI; ++a) av[a] = A[(ty + 16 * a) * lda + k];
+#pragma unroll
+        for (int c = 0; c < NJ; ++c) bv[c] = Bm[k * ldb + tx + 16 * c];
+#pragma unroll
+        for (int a = 0; a < MI; ++a)
+#pragma unroll
+            for (int c = 0; c < NJ; ++c) acc[a][c] = fma(av[a], bv[c], acc[a][c]);
+    }
+}
+
+// B[i][k] -= sum_{m < 32} B[i][o + m] B[k][o + m]  for i, k in [o + 32, 128): NA = (96 - o) / 16 row / column groups per thread
+template <int NA>
+__device__ __forceinline__ void diag_trailing_update(double* B, int o, int ty, int tx) {
+    double acc[NA][NA];
+#pragma unroll
+    for (int a = 0; a < NA; ++a)
+#pragma unroll
+        for (int c = 0; c < NA; ++c) acc[a][c] = 0.0;
+    const double* ri = B + (o + kSB + ty) * kDiagLd + o;
+    const double* rk = B + (o + kSB + tx) * kDiagLd + o;
+#pragma unroll 4
+    for (int m = 0; m < kSB; ++m) {
+        double xi[NA], xk[NA];
+#pragma unroll
+        for (int a = 0; a < NA; ++a) xi[a] = ri[16 * a * kDiagLd + m];
+#pragma unroll
+        for (int c = 0; c < NA; ++c) xk[c] = rk[16 * c * kDiagLd + m];
+#pragma unroll
+        for (int a = 0; a < NA; ++a)
+#pragma unroll
+            for (int c = 0; c < NA; ++c) acc[a][c] = fma(xi[a], xk[c], acc[a][c]);
+    }
+#pragma unroll
+    for (int a = 0; a < NA; ++a)
+#pragma unroll
+        for (int c = 0; c < NA; ++c) B[(o + kSB + ty + 16 * a) * kDiagLd + o + kSB + tx + 16 * c] -= acc[a][c];
+}
+
 __global__ void __launch_bounds__(256, 1)
 potrf_diag_kernel(double* __restrict__ A, int ld, int p, double* __restrict__ Linv, double* __restrict__ Wt, int* __restrict__ info) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* B = reinterpret_cast<double*>(smem_raw);          // kFB x kDiagLd
-    double* col = B + kFB * kDiagLd;                            // kFB: the column being eliminated by the inverse
+    double* B = reinterpret_cast<double*>(smem_raw);          // kFB x kDiagLd: the block; L after phase A; W = L^-1 after phase B
+    double* Wd = B + kFB * kDiagLd;                             // 4 x (32 x 33): inverses of the diagonal sub-blocks
+    double* T = Wd + 4 * kSB * kSubLd;                          // 64 x 65: scratch product of phase B
+    double* invd = T + 2 * kSB * kHalfLd;                       // 32: reciprocal diagonal of the current sub-block
     __shared__ int fail;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ty = tid >> 4, tx = tid & 15;
     double* __restrict__ blk = A + (size_t)p * kFB * ld + (size_t)p * kFB;
     for (int e = tid; e < kFB * kFB; e += 256) B[(e / kFB) * kDiagLd + (e % kFB)] = blk[(size_t)(e / kFB) * ld + (e % kFB)];
     if (tid == 0) fail = 0;
     __syncthreads();
-    // right-looking Cholesky, lower
-    for (int j = 0; j < kFB; ++j) {
-        if (tid == 0) {
-            const double piv = B[j * kDiagLd + j];
-            if (!(piv > 0.0)) fail = 1;
-            B[j * kDiagLd + j] = sqrt(piv);
+
+    // ---- phase A
+#pragma unroll 1
+    for (int b = 0; b < kFB / kSB; ++b) {
+        const int o = b * kSB;
+        if (warp == 0) {
+            double a[kSB];
+            double* row = B + (o + lane) * kDiagLd + o;
+#pragma unroll
+            for (int k = 0; k < kSB; ++k) a[k] = row[k];
+            bool bad = false;
+#pragma unroll
+            for (int j = 0; j < kSB; ++j) {
+                const double piv = __shfl_sync(0xffffffffu, a[j], j);
+                bad |= !(piv > 0.0);
+                const double inv = rsqrt(piv);
+                a[j] = lane == j ? piv * inv : a[j] * inv;        // lanes < j hold the (unused) upper part
+                if (lane == j) invd[j] = inv;
+#pragma unroll
+                for (int k = j + 1; k < kSB; ++k) a[k] = fma(-a[j], __shfl_sync(0xffffffffu, a[j], k), a[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < kSB; ++k)
+                if (k <= lane) row[k] = a[k];
+            if (bad && lane == 0) fail = 1;
         }
         __syncthreads();
-        if (fail) break;
-        const double inv = 1.0 / B[j * kDiagLd + j];
-        for (int i = j + 1 + tid; i < kFB; i += 256) B[i * kDiagLd + j] *= inv;
-        __syncthreads();
-        for (int i = j + 1 + (tid >> 4); i < kFB; i += 16) {      // 16 x 16 threads over (row i, column k <= i)
-            const double lij = B[i * kDiagLd + j];
-            for (int k = j + 1 + (tid & 15); k <= i; k += 16) B[i * kDiagLd + k] = fma(-lij, B[k * kDiagLd + j], B[i * kDiagLd + k]);
+        if (warp == 4) {
+            // column `lane` of L_bb^-1:  x[i] = (delta_{i,lane} - sum_{k < i} L[i][k] x[k]) / L[i][i]
+            double x[kSB];
+            const double* Lb = B + o * kDiagLd + o;
+#pragma unroll
+            for (int i = 0; i < kSB; ++i) {
+                double s0 = i == lane ? 1.0 : 0.0, s1 = 0.0;
+#pragma unroll
+                for (int k = 0; k + 1 < i; k += 2) {
+                    s0 = fma(-Lb[i * kDiagLd + k], x[k], s0);
+                    s1 = fma(-Lb[i * kDiagLd + k + 1], x[k + 1], s1);
+                }
+                if (i & 1) s0 = fma(-Lb[i * kDiagLd + i - 1], x[i - 1], s0);
+                x[i] = (s0 + s1) * invd[i];
+                Wd[(b * kSB + i) * kSubLd + lane] = x[i];
+            }
+        } else if (warp >= 1 && warp <= 3) {
+            const int r = o + kSB + (tid - 32);
+            if (r < kFB) {
+                double x[kSB];
+                double* row = B + r * kDiagLd + o;
+                const double* Lb = B + o * kDiagLd + o;
+#pragma unroll
+                for (int k = 0; k < kSB; ++k) {
+                    double s0 = row[k], s1 = 0.0;
+#pragma unroll
+                    for (int m = 0; m + 1 < k; m += 2) {
+                        s0 = fma(-x[m], Lb[k * kDiagLd + m], s0);
+                        s1 = fma(-x[m + 1], Lb[k * kDiagLd + m + 1], s1);
+                    }
+                    if (k & 1) s0 = fma(-x[k - 1], Lb[k * kDiagLd + k - 1], s0);
+                    x[k] = (s0 + s1) * invd[k];
+                }
+#pragma unroll
+                for (int k = 0; k < kSB; ++k) row[k] = x[k];
+            }
         }
+        __syncthreads();
+        if (b == 0) diag_trailing_update<6>(B, o, ty, tx);
+        else if (b == 1) diag_trailing_update<4>(B, o, ty, tx);
+        else if (b == 2) diag_trailing_update<2>(B, o, ty, tx);
         __syncthreads();
     }
     if (fail) {
-        if (tid == 0 && atomicCAS(info, 0, 1 + p) == 0) {}
+        if (tid == 0) atomicCAS(info, 0, 1 + p);
         const double nan = __longlong_as_double(0x7ff8000000000000LL);
         for (int e = tid; e < kFB * kFB; e += 256) {
             const int i = e / kFB, j = e % kFB;
@@ -108,18 +227,49 @@ potrf_diag_kernel(double* __restrict__ A, int ld, int p, double* __restrict__ Li
         blk[(size_t)i * ld + j] = j <= i ? B[i * kDiagLd + j] : 0.0;
     }
     __syncthreads();
-    // in-place inverse of the lower-triangular block, last column first (LAPACK dtrti2, lower):
-    //   W[j][j] = 1 / L[j][j] ;  W[j+1:, j] = -W[j+1:, j+1:] L[j+1:, j] W[j][j]
-    for (int j = kFB - 1; j >= 0; --j) {
-        if (tid == 0) B[j * kDiagLd + j] = 1.0 / B[j * kDiagLd + j];
-        for (int i = j + 1 + tid; i < kFB; i += 256) col[i] = B[i * kDiagLd + j];
-        __syncthreads();
-        const double wjj = B[j * kDiagLd + j];
-        for (int i = j + 1 + tid; i < kFB; i += 256) {
-            double acc = 0.0;
-            for (int k = j + 1; k <= i; ++k) acc = fma(B[i * kDiagLd + k], col[k], acc);
-            B[i * kDiagLd + j] = -acc * wjj;
+
+    // ---- phase B: B's diagonal sub-blocks <- Wd, the upper sub-blocks (0,1) and (2,3) <- 0, then the recursion
+    for (int e = tid; e < 4 * kSB * kSB; e += 256) {
+        const int b = e / (kSB * kSB), i = (e / kSB) % kSB, j = e % kSB;
+        B[(b * kSB + i) * kDiagLd + b * kSB + j] = Wd[(b * kSB + i) * kSubLd + j];
+        if (!(b & 1)) B[(b * kSB + i) * kDiagLd + (b + 1) * kSB + j] = 0.0;
+    }
+    {   // level 1: W[b1,b0] = -Wd[b1] (L[b1,b0] Wd[b0]) for (b0, b1) = (0, 1), (2, 3)
+        double acc[2][2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int b0 = 2 * h, b1 = b0 + 1;
+            smem_product<2, 2>(acc, B + (b1 * kSB) * kDiagLd + b0 * kSB, kDiagLd, Wd + b0 * kSB * kSubLd, kSubLd, kSB, ty, tx);
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) T[(h * kSB + ty + 16 * a) * kSubLd + tx + 16 * c] = acc[a][c];
         }
+        __syncthreads();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int b0 = 2 * h, b1 = b0 + 1;
+            smem_product<2, 2>(acc, Wd + b1 * kSB * kSubLd, kSubLd, T + h * kSB * kSubLd, kSubLd, kSB, ty, tx);
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) B[(b1 * kSB + ty + 16 * a) * kDiagLd + b0 * kSB + tx + 16 * c] = -acc[a][c];
+        }
+        __syncthreads();
+    }
+    {   // level 2: W21 = -W22 (L21 W11) on the 64-wide halves
+        double acc[4][4];
+        smem_product<4, 4>(acc, B + 2 * kSB * kDiagLd, kDiagLd, B, kDiagLd, 2 * kSB, ty, tx);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) T[(ty + 16 * a) * kHalfLd + tx + 16 * c] = acc[a][c];
+        __syncthreads();
+        smem_product<4, 4>(acc, B + 2 * kSB * kDiagLd + 2 * kSB, kDiagLd, T, kHalfLd, 2 * kSB, ty, tx);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) B[(2 * kSB + ty + 16 * a) * kDiagLd + tx + 16 * c] = -acc[a][c];
         __syncthreads();
     }
     for (int e = tid; e < kFB * kFB; e += 256) {
@@ -167,21 +317,20 @@ trsm_panel_kernel(double* __restrict__ A, int ld, int p, const double* __restric
     });
 }
 
-// A[I,J] -= A[I,p] A[J,p]^T for the lower block triangle behind panel p
+// A[I,q] -= A[I,p0..q-1] A[q,p0..q-1]^T for I = q + blockIdx.x (the diagonal tile included): the left-looking update of block
+// column q by the columns of its own panel that are already factored
 __global__ void __launch_bounds__(256, 1)
-syrk_update_kernel(double* __restrict__ A, int ld, int p) {
+chol_colupdate_kernel(double* __restrict__ A, int ld, int p0, int q) {
     CBO_FIT_TILE_PROLOGUE();
-    int bi, bj;
-    tri_tile(blockIdx.x, bi, bj);
-    const int I = p + 1 + bi, J = p + 1 + bj;
-    abt_mainloop<2, 4, 8, 4, kFitStages>(A + (size_t)I * kFB * ld + (size_t)p * kFB, ld, A + (size_t)J * kFB * ld + (size_t)p * kFB, ld,
-                                         kFB / kBK, sA, sB, acc, tid);
-    double* __restrict__ blk = A + (size_t)I * kFB * ld + (size_t)J * kFB;
+    const int I = q + blockIdx.x;
+    abt_mainloop<2, 4, 8, 4, kFitStages>(A + (size_t)I * kFB * ld + (size_t)p0 * kFB, ld, A + (size_t)q * kFB * ld + (size_t)p0 * kFB, ld,
+                                         (q - p0) * (kFB / kBK), sA, sB, acc, tid);
+    double* __restrict__ blk = A + (size_t)I * kFB * ld + (size_t)q * kFB;
     for_each_acc(acc, tid, [&](int r, int c, double v0, double v1) {
-        double2* q = reinterpret_cast<double2*>(blk + (size_t)r * ld + c);
-        double2 o = *q;
+        double2* o2 = reinterpret_cast<double2*>(blk + (size_t)r * ld + c);
+        double2 o = *o2;
         o.x -= v0, o.y -= v1;
-        *q = o;
+        *o2 = o;
     });
 }
 
@@ -197,14 +346,16 @@ winv_scale_kernel(double* __restrict__ Wt, int ld, int K, const double* __restri
     });
 }
 
-// Wt[J,I] -= Wt[J,K] L[I,K]^T for I = K + 1 + blockIdx.x, J = blockIdx.y <= K: the running right-hand side of the rows below K
+// Wt[J,K] -= Wt[J,P] L[K,P]^T for the block column K inside a panel whose earlier columns P = K0 .. K - 1 are final; J = blockIdx.x
+// < K.  Wt is upper triangular: the product starts at block max(J, K0).
 __global__ void __launch_bounds__(256, 1)
-winv_update_kernel(const double* __restrict__ L, double* __restrict__ Wt, int ld, int K) {
+winv_colupdate_kernel(const double* __restrict__ L, double* __restrict__ Wt, int ld, int K0, int K) {
     CBO_FIT_TILE_PROLOGUE();
-    const int I = K + 1 + blockIdx.x, J = blockIdx.y;
-    abt_mainloop<2, 4, 8, 4, kFitStages>(Wt + (size_t)J * kFB * ld + (size_t)K * kFB, ld, L + (size_t)I * kFB * ld + (size_t)K * kFB, ld,
-                                         kFB / kBK, sA, sB, acc, tid);
-    double* __restrict__ blk = Wt + (size_t)J * kFB * ld + (size_t)I * kFB;
+    const int J = blockIdx.x;
+    const int k0 = J > K0 ? J : K0;
+    abt_mainloop<2, 4, 8, 4, kFitStages>(Wt + (size_t)J * kFB * ld + (size_t)k0 * kFB, ld, L + (size_t)K * kFB * ld + (size_t)k0 * kFB, ld,
+                                         (K - k0) * (kFB / kBK), sA, sB, acc, tid);
+    double* __restrict__ blk = Wt + (size_t)J * kFB * ld + (size_t)K * kFB;
     for_each_acc(acc, tid, [&](int r, int c, double v0, double v1) {
         double2* q = reinterpret_cast<double2*>(blk + (size_t)r * ld + c);
         double2 o = *q;
@@ -213,27 +364,73 @@ winv_update_kernel(const double* __restrict__ L, double* __restrict__ Wt, int ld
     });
 }
 
-// Ky^-1[i][j] = sum_{k >= max(i,j)} Wt[i][k] Wt[j][k]; live N x N corner, row pitch n, both triangles
-__global__ void __launch_bounds__(256, 1)
-kyinv_kernel(const double* __restrict__ Wt, int ld, int n, double* __restrict__ kyinv) {
-    CBO_FIT_TILE_PROLOGUE();
-    int I, J;
-    tri_tile(blockIdx.x, I, J);
-    const int nb = ld / kFB;
-    abt_mainloop<2, 4, 8, 4, kFitStages>(Wt + (size_t)I * kFB * ld + (size_t)I * kFB, ld, Wt + (size_t)J * kFB * ld + (size_t)I * kFB, ld,
-                                         (nb - I) * (kFB / kBK), sA, sB, acc, tid);
-    for_each_acc(acc, tid, [&](int r, int c, double v0, double v1) {
-        const int i = I * kFB + r, j = J * kFB + c;
-        if (i < n) {
-            if (j < n) kyinv[(size_t)i * n + j] = v0;
-            if (j + 1 < n) kyinv[(size_t)i * n + j + 1] = v1;
-            if (I != J) {
-                if (j < n) kyinv[(size_t)j * n + i] = v0;
-                if (j + 1 < n) kyinv[(size_t)(j + 1) * n + i] = v1;
-            }
-        }
+// ---- the three large tile products on the TMA pipeline (dmma_tma_tile.cuh) ------------------------------------------------
+__device__ __forceinline__ void tile_subtract(double* __restrict__ blk, size_t ld, const double (&acc)[8][4][2], int tid) {
+    tma_for_each_acc(acc, tid, [&](int r, int c, double v0, double v1) {
+        double2* q = reinterpret_cast<double2*>(blk + (size_t)r * ld + c);
+        double2 o = *q;
+        o.x -= v0, o.y -= v1;
+        *q = o;
     });
 }
+
+// A[I,J] -= A[I,P] A[J,P]^T, P = block columns p0 .. p0 + w - 1, lower block triangle behind the panel (T block rows)
+struct SyrkPlan {
+    double* A;
+    int ld, p0, w, T;
+    __device__ int count() const { return T * (T + 1) / 2; }
+    __device__ TileJob job(int t) const {
+        int bi, bj;
+        tri_tile(t, bi, bj);
+        return TileJob{(p0 + w + bi) * kFB, (p0 + w + bj) * kFB, p0 * kFB, w * (kFB / kBK), p0 + w + bi, p0 + w + bj};
+    }
+    __device__ void store(const TileJob& j, const double (&acc)[8][4][2], int tid) const {
+        tile_subtract(A + (size_t)j.ti * kFB * ld + (size_t)j.tj * kFB, ld, acc, tid);
+    }
+};
+
+// Wt[J,I] -= Wt[J,P] L[I,P]^T for the T block columns I behind the panel P = K0 .. K0 + w - 1 and every J < K0 + w; the product
+// starts at block max(J, K0) (Wt is upper triangular).  Rows J of the panel itself (the short products) come last.
+struct WinvPlan {
+    double* Wt;
+    int ld, K0, w, T;
+    __device__ int count() const { return T * (K0 + w); }
+    __device__ TileJob job(int t) const {
+        const int J = t / T, I = K0 + w + t % T;
+        const int k0 = J > K0 ? J : K0;
+        return TileJob{J * kFB, I * kFB, k0 * kFB, (K0 + w - k0) * (kFB / kBK), J, I};
+    }
+    __device__ void store(const TileJob& j, const double (&acc)[8][4][2], int tid) const {
+        tile_subtract(Wt + (size_t)j.ti * kFB * ld + (size_t)j.tj * kFB, ld, acc, tid);
+    }
+};
+
+// Ky^-1[i][j] = sum_{k >= max(i,j)} Wt[i][k] Wt[j][k]; live N x N corner, row pitch n, both triangles.  Tiles in the order of
+// tri_tile: block row I = 0 (the deepest products) first.
+struct KyinvPlan {
+    double* kyinv;
+    int n, nb;
+    __device__ int count() const { return nb * (nb + 1) / 2; }
+    __device__ TileJob job(int t) const {
+        int I, J;
+        tri_tile(t, I, J);
+        return TileJob{I * kFB, J * kFB, I * kFB, (nb - I) * (kFB / kBK), I, J};
+    }
+    __device__ void store(const TileJob& jb, const double (&acc)[8][4][2], int tid) const {
+        const int I = jb.ti, J = jb.tj;
+        tma_for_each_acc(acc, tid, [&](int r, int c, double v0, double v1) {
+            const int i = I * kFB + r, j = J * kFB + c;
+            if (i < n) {
+                if (j < n) kyinv[(size_t)i * n + j] = v0;
+                if (j + 1 < n) kyinv[(size_t)i * n + j + 1] = v1;
+                if (I != J) {
+                    if (j < n) kyinv[(size_t)j * n + i] = v0;
+                    if (j + 1 < n) kyinv[(size_t)(j + 1) * n + i] = v1;
+                }
+            }
+        });
+    }
+};
 
 // z[k] = sum_{i <= k} Wt[i][k] y[i]: grid (column tile, row chunk); a thread owns one column of one chunk of 256 rows and
 // writes one partial; wty_reduce_kernel adds the chunks in order (deterministic)
@@ -339,6 +536,16 @@ nll_reduce_kernel(const double* __restrict__ part, int n, int D, const double* _
     }
 }
 
+// Panel width of the blocked factorisation, in 128-column blocks (CBO_FIT_PANEL overrides the default for tuning runs).
+static int fit_panel_blocks() {
+    static const int w = [] {
+        const char* e = getenv("CBO_FIT_PANEL");
+        const int v = e ? atoi(e) : 4;
+        return v < 1 ? 1 : (v > 16 ? 16 : v);
+    }();
+    return w;
+}
+
 static size_t fit_ws_doubles(int npad) {
     const size_t nb = npad / kFB, chunks = (npad + kWtyRows - 1) / kWtyRows;
     const size_t zpart = (size_t)npad * chunks, nllpart = (size_t)npad * kNllTerms;        // the two never live together
@@ -358,14 +565,16 @@ size_t obs_gp_workspace_bytes_impl(const cbo_set_desc* h_sets, int num_sets) {
 int obs_gp_fit_impl(const cbo_set_desc* h_sets, int num_sets, double jitter, void* d_ws, size_t ws_bytes, int32_t* d_info,
                     cudaStream_t st) {
     constexpr size_t TILE_SMEM = (size_t)kFitStages * 2 * kFB * kBK * sizeof(double);
-    constexpr size_t DIAG_SMEM = ((size_t)kFB * kDiagLd + kFB) * sizeof(double);
+    constexpr size_t DIAG_SMEM = kDiagSmemDoubles * sizeof(double);
     CBO_CUDA(allow_dynamic_smem(potrf_diag_kernel, DIAG_SMEM));
     CBO_CUDA(allow_dynamic_smem(trsm_panel_kernel, TILE_SMEM));
-    CBO_CUDA(allow_dynamic_smem(syrk_update_kernel, TILE_SMEM));
+    CBO_CUDA(allow_dynamic_smem(chol_colupdate_kernel, TILE_SMEM));
     CBO_CUDA(allow_dynamic_smem(winv_scale_kernel, TILE_SMEM));
-    CBO_CUDA(allow_dynamic_smem(winv_update_kernel, TILE_SMEM));
-    CBO_CUDA(allow_dynamic_smem(kyinv_kernel, TILE_SMEM));
+    CBO_CUDA(allow_dynamic_smem(winv_colupdate_kernel, TILE_SMEM));
     CBO_REQUIRE(d_info != nullptr, "cbo_obs_gp_fit: d_info is NULL");
+    int dev = 0, sms = 0;
+    CBO_CUDA(cudaGetDevice(&dev));
+    CBO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     for (int s = 0; s < num_sets; ++s) {
         const cbo_set_desc& S = h_sets[s];
         if (!computes_prior(S) || !S.y_obs) continue;
@@ -382,6 +591,8 @@ int obs_gp_fit_impl(const cbo_set_desc* h_sets, int num_sets, double jitter, voi
         const int chunks = (npad + kWtyRows - 1) / kWtyRows;
         int* info = d_info + s;
         CBO_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
+        CUtensorMap mapA, mapW;
+        if (make_f64_rowmajor_map(&mapA, A, npad, npad, npad) || make_f64_rowmajor_map(&mapW, Wt, npad, npad, npad)) return -1;
         ObsX X;
         X.D = S.d + S.c;
         for (int k = 0; k < CBO_MAX_D + CBO_MAX_C; ++k) {
@@ -392,31 +603,44 @@ int obs_gp_fit_impl(const cbo_set_desc* h_sets, int num_sets, double jitter, voi
         gram_kernel<<<dim3((npad + 255) / 256 < 8 ? (npad + 255) / 256 : 8, npad), 256, 0, st>>>(X, n, npad, S.s2,
                                                                                                S.noise + 1e-8 + jitter, A);
         note_launch();
-        for (int p = 0; p < nb; ++p) {
-            potrf_diag_kernel<<<1, 256, DIAG_SMEM, st>>>(A, npad, p, Linv + (size_t)p * kFB * kFB, Wt, info);
-            note_launch();
-            const int T = nb - p - 1;
-            if (T > 0) {
-                trsm_panel_kernel<<<T, 256, TILE_SMEM, st>>>(A, npad, p, Linv + (size_t)p * kFB * kFB);
+        // Cholesky: panels of W block columns.  Inside a panel each block column is first brought up to date against the panel's
+        // earlier columns (left-looking, one wave of tiles), then factored; the trailing matrix takes ONE 128 W deep update per
+        // panel, so its tiles run a W times longer mainloop per read-modify-write of C than a 128-deep right-looking update.
+        const int W = fit_panel_blocks();
+        for (int p0 = 0; p0 < nb; p0 += W) {
+            const int we = nb - p0 < W ? nb - p0 : W;
+            for (int q = p0; q < p0 + we; ++q) {
+                if (q > p0) {
+                    chol_colupdate_kernel<<<nb - q, 256, TILE_SMEM, st>>>(A, npad, p0, q);
+                    note_launch();
+                }
+                potrf_diag_kernel<<<1, 256, DIAG_SMEM, st>>>(A, npad, q, Linv + (size_t)q * kFB * kFB, Wt, info);
                 note_launch();
-                syrk_update_kernel<<<T * (T + 1) / 2, 256, TILE_SMEM, st>>>(A, npad, p);
-                note_launch();
+                if (nb - q - 1 > 0) {
+                    trsm_panel_kernel<<<nb - q - 1, 256, TILE_SMEM, st>>>(A, npad, q, Linv + (size_t)q * kFB * kFB);
+                    note_launch();
+                }
             }
+            const int T = nb - p0 - we;
+            if (T > 0) CBO_CUDA(launch_tma_tiles(mapA, mapA, SyrkPlan{A, npad, p0, we, T}, T * (T + 1) / 2, sms, st));
         }
-        for (int K = 0; K + 1 < nb; ++K) {
-            if (K > 0) {
-                winv_scale_kernel<<<K, 256, TILE_SMEM, st>>>(Wt, npad, K, Linv + (size_t)K * kFB * kFB);
-                note_launch();
+        // triangular inverse, same panel scheme on the transposes
+        for (int K0 = 0; K0 < nb; K0 += W) {
+            const int we = nb - K0 < W ? nb - K0 : W;
+            for (int K = K0; K < K0 + we; ++K) {
+                if (K > K0) {
+                    winv_colupdate_kernel<<<K, 256, TILE_SMEM, st>>>(A, Wt, npad, K0, K);
+                    note_launch();
+                }
+                if (K > 0) {
+                    winv_scale_kernel<<<K, 256, TILE_SMEM, st>>>(Wt, npad, K, Linv + (size_t)K * kFB * kFB);
+                    note_launch();
+                }
             }
-            winv_update_kernel<<<dim3(nb - K - 1, K + 1), 256, TILE_SMEM, st>>>(A, Wt, npad, K);
-            note_launch();
+            const int T = nb - K0 - we;
+            if (T > 0) CBO_CUDA(launch_tma_tiles(mapW, mapA, WinvPlan{Wt, npad, K0, we, T}, T * (K0 + we), sms, st));
         }
-        if (nb > 1) {
-            winv_scale_kernel<<<nb - 1, 256, TILE_SMEM, st>>>(Wt, npad, nb - 1, Linv + (size_t)(nb - 1) * kFB * kFB);
-            note_launch();
-        }
-        kyinv_kernel<<<nb * (nb + 1) / 2, 256, TILE_SMEM, st>>>(Wt, npad, n, const_cast<double*>(S.kyinv));
-        note_launch();
+        CBO_CUDA(launch_tma_tiles(mapW, mapW, KyinvPlan{const_cast<double*>(S.kyinv), n, nb}, nb * (nb + 1) / 2, sms, st));
         wty_kernel<<<dim3(npad / 128, chunks), 128, 0, st>>>(Wt, npad, n, S.y_obs, zpart);
         note_launch();
         wty_reduce_kernel<<<npad / 128, 128, 0, st>>>(zpart, npad, chunks, z);
