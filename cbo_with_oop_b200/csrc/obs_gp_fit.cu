@@ -280,88 +280,79 @@ potrf_diag_kernel(double* __restrict__ A, int ld, int p, double* __restrict__ Li
     }
 }
 
-// acc fragment -> (row, column) of the 128 x 128 tile: acc[mi][ni][e] is element (row0 + mi*8 + lane/4, col0 + ni*8 + (lane%4)*2 + e)
-template <class F>
-__device__ __forceinline__ void for_each_acc(const double (&acc)[8][4][2], int tid, F&& f) {
-    const int lane = tid & 31, warp = tid >> 5;
-    const int row0 = (warp / 4) * 64, col0 = (warp % 4) * 32;
+// ---- the one-wave tile products inside a panel ----------------------------------------------------------------------------
+// Four updates run on at most nb - 1 <= 78 output tiles of 128 x 128 at a time, fewer than the GPU has SMs, and sit on the
+// critical path between the diagonal-block kernels:
+//   trsm      A[I,q]  <- A[I,q] Linv_q^T                       I > q                (the rows below the diagonal block)
+//   colupdate A[I,q]  -= A[I,P] A[q,P]^T                        I >= q, P = p0..q-1  (left-looking, inside the panel)
+//   scale     Wt[J,K] <- Wt[J,K] Linv_K^T                       J < K                (block row K of W = L^-1 becomes final)
+//   wcolupdate Wt[J,K] -= Wt[J,P] L[K,P]^T                      J < K, P = max(J,K0)..K-1
+// One kernel serves all four: tile t reads the rows a0 + t * a_step (pitch lda) against the rows b0 (pitch ldb) and writes or
+// subtracts at c0 + t * c_step.  The 128 output rows of a tile are SPLIT over 128 / (16 MA) CTAs (MA = 8, 4, 2: 128, 64 or 32
+// rows each) so that a wave of few tiles still covers the SMs; rows are independent, so the in-place forms stay race free.
+struct PanelOp {
+    const double* a0;
+    const double* b0;
+    double* c0;
+    size_t a_step, c_step, lda, ldb, ldc;
+    int nk;          // depth in 16-deep slabs
+    int subtract;    // C -= product (else C = product)
+    int tri_base;    // >= 0: tile t skips the leading max(t - tri_base, 0) blocks of the product (Wt is upper triangular)
+};
+
+template <int MA>
+__global__ void __launch_bounds__(256, 1)
+panel_tile_kernel(const PanelOp op) {
+    constexpr int ROWS = 16 * MA, SPLIT = kFB / ROWS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* sA = reinterpret_cast<double*>(smem_raw);
+    double* sB = sA + kFitStages * ROWS * kBK;
+    const int tid = threadIdx.x;
+    const int t = blockIdx.x / SPLIT, sub = blockIdx.x % SPLIT;
+    double acc[MA][4][2];
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi) {
+    for (int mi = 0; mi < MA; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    const int skip = op.tri_base >= 0 && t > op.tri_base ? t - op.tri_base : 0;
+    const double* gA = op.a0 + (size_t)t * op.a_step + (size_t)sub * ROWS * op.lda + (size_t)skip * kFB;
+    const double* gB = op.b0 + (size_t)skip * kFB;
+    abt_mainloop<2, 4, MA, 4, kFitStages>(gA, op.lda, gB, op.ldb, op.nk - skip * (kFB / kBK), sA, sB, acc, tid);
+    double* __restrict__ blk = op.c0 + (size_t)t * op.c_step + (size_t)sub * ROWS * op.ldc;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int row0 = (warp / 4) * MA * 8, col0 = (warp % 4) * 32;
+#pragma unroll
+    for (int mi = 0; mi < MA; ++mi) {
         const int r = row0 + mi * 8 + (lane >> 2);
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) {
-            const int c = col0 + ni * 8 + (lane & 3) * 2;
-            f(r, c, acc[mi][ni][0], acc[mi][ni][1]);
+            double2* q = reinterpret_cast<double2*>(blk + (size_t)r * op.ldc + col0 + ni * 8 + (lane & 3) * 2);
+            double2 o = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+            if (op.subtract) {
+                const double2 old = *q;
+                o.x = old.x - o.x, o.y = old.y - o.y;
+            }
+            *q = o;
         }
     }
 }
 
-#define CBO_FIT_TILE_PROLOGUE()                                                       \
-    extern __shared__ __align__(16) unsigned char smem_raw[];                         \
-    double* sA = reinterpret_cast<double*>(smem_raw);                                 \
-    double* sB = sA + kFitStages * kFB * kBK;                                         \
-    const int tid = threadIdx.x;                                                      \
-    double acc[8][4][2];                                                              \
-    _Pragma("unroll") for (int mi = 0; mi < 8; ++mi)                                  \
-        _Pragma("unroll") for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-
-// A[I,p] <- A[I,p] Linv_p^T for I = p + 1 + blockIdx.x
-__global__ void __launch_bounds__(256, 1)
-trsm_panel_kernel(double* __restrict__ A, int ld, int p, const double* __restrict__ Linv) {
-    CBO_FIT_TILE_PROLOGUE();
-    const int I = p + 1 + blockIdx.x;
-    double* __restrict__ blk = A + (size_t)I * kFB * ld + (size_t)p * kFB;
-    abt_mainloop<2, 4, 8, 4, kFitStages>(blk, ld, Linv, kFB, kFB / kBK, sA, sB, acc, tid);
-    for_each_acc(acc, tid, [&](int r, int c, double v0, double v1) {
-        *reinterpret_cast<double2*>(blk + (size_t)r * ld + c) = make_double2(v0, v1);
-    });
-}
-
-// A[I,q] -= A[I,p0..q-1] A[q,p0..q-1]^T for I = q + blockIdx.x (the diagonal tile included): the left-looking update of block
-// column q by the columns of its own panel that are already factored
-__global__ void __launch_bounds__(256, 1)
-chol_colupdate_kernel(double* __restrict__ A, int ld, int p0, int q) {
-    CBO_FIT_TILE_PROLOGUE();
-    const int I = q + blockIdx.x;
-    abt_mainloop<2, 4, 8, 4, kFitStages>(A + (size_t)I * kFB * ld + (size_t)p0 * kFB, ld, A + (size_t)q * kFB * ld + (size_t)p0 * kFB, ld,
-                                         (q - p0) * (kFB / kBK), sA, sB, acc, tid);
-    double* __restrict__ blk = A + (size_t)I * kFB * ld + (size_t)q * kFB;
-    for_each_acc(acc, tid, [&](int r, int c, double v0, double v1) {
-        double2* o2 = reinterpret_cast<double2*>(blk + (size_t)r * ld + c);
-        double2 o = *o2;
-        o.x -= v0, o.y -= v1;
-        *o2 = o;
-    });
-}
-
-// Wt[J,K] <- Wt[J,K] Linv_K^T for J = blockIdx.x < K: block row K of W = L^-1 becomes final (held transposed)
-__global__ void __launch_bounds__(256, 1)
-winv_scale_kernel(double* __restrict__ Wt, int ld, int K, const double* __restrict__ Linv) {
-    CBO_FIT_TILE_PROLOGUE();
-    const int J = blockIdx.x;
-    double* __restrict__ blk = Wt + (size_t)J * kFB * ld + (size_t)K * kFB;
-    abt_mainloop<2, 4, 8, 4, kFitStages>(blk, ld, Linv, kFB, kFB / kBK, sA, sB, acc, tid);   // acc[n][m] = sum_k R^T[n][k] Linv[m][k]
-    for_each_acc(acc, tid, [&](int r, int c, double v0, double v1) {
-        *reinterpret_cast<double2*>(blk + (size_t)r * ld + c) = make_double2(v0, v1);
-    });
-}
-
-// Wt[J,K] -= Wt[J,P] L[K,P]^T for the block column K inside a panel whose earlier columns P = K0 .. K - 1 are final; J = blockIdx.x
-// < K.  Wt is upper triangular: the product starts at block max(J, K0).
-__global__ void __launch_bounds__(256, 1)
-winv_colupdate_kernel(const double* __restrict__ L, double* __restrict__ Wt, int ld, int K0, int K) {
-    CBO_FIT_TILE_PROLOGUE();
-    const int J = blockIdx.x;
-    const int k0 = J > K0 ? J : K0;
-    abt_mainloop<2, 4, 8, 4, kFitStages>(Wt + (size_t)J * kFB * ld + (size_t)k0 * kFB, ld, L + (size_t)K * kFB * ld + (size_t)k0 * kFB, ld,
-                                         (K - k0) * (kFB / kBK), sA, sB, acc, tid);
-    double* __restrict__ blk = Wt + (size_t)J * kFB * ld + (size_t)K * kFB;
-    for_each_acc(acc, tid, [&](int r, int c, double v0, double v1) {
-        double2* q = reinterpret_cast<double2*>(blk + (size_t)r * ld + c);
-        double2 o = *q;
-        o.x -= v0, o.y -= v1;
-        *q = o;
-    });
+static cudaError_t launch_panel_op(const PanelOp& op, int tiles, int sms, cudaStream_t st) {
+    constexpr size_t SMEM = (size_t)kFitStages * 2 * kFB * kBK * sizeof(double);
+    if (tiles <= 0) return cudaSuccess;
+    cudaError_t e;
+    if (4 * tiles <= sms) {
+        if ((e = allow_dynamic_smem(panel_tile_kernel<2>, SMEM)) != cudaSuccess) return e;
+        panel_tile_kernel<2><<<4 * tiles, 256, SMEM, st>>>(op);
+    } else if (2 * tiles <= sms) {
+        if ((e = allow_dynamic_smem(panel_tile_kernel<4>, SMEM)) != cudaSuccess) return e;
+        panel_tile_kernel<4><<<2 * tiles, 256, SMEM, st>>>(op);
+    } else {
+        if ((e = allow_dynamic_smem(panel_tile_kernel<8>, SMEM)) != cudaSuccess) return e;
+        panel_tile_kernel<8><<<tiles, 256, SMEM, st>>>(op);
+    }
+    note_launch();
+    return cudaGetLastError();
 }
 
 // ---- the three large tile products on the TMA pipeline (dmma_tma_tile.cuh) ------------------------------------------------
@@ -564,13 +555,8 @@ size_t obs_gp_workspace_bytes_impl(const cbo_set_desc* h_sets, int num_sets) {
 
 int obs_gp_fit_impl(const cbo_set_desc* h_sets, int num_sets, double jitter, void* d_ws, size_t ws_bytes, int32_t* d_info,
                     cudaStream_t st) {
-    constexpr size_t TILE_SMEM = (size_t)kFitStages * 2 * kFB * kBK * sizeof(double);
     constexpr size_t DIAG_SMEM = kDiagSmemDoubles * sizeof(double);
     CBO_CUDA(allow_dynamic_smem(potrf_diag_kernel, DIAG_SMEM));
-    CBO_CUDA(allow_dynamic_smem(trsm_panel_kernel, TILE_SMEM));
-    CBO_CUDA(allow_dynamic_smem(chol_colupdate_kernel, TILE_SMEM));
-    CBO_CUDA(allow_dynamic_smem(winv_scale_kernel, TILE_SMEM));
-    CBO_CUDA(allow_dynamic_smem(winv_colupdate_kernel, TILE_SMEM));
     CBO_REQUIRE(d_info != nullptr, "cbo_obs_gp_fit: d_info is NULL");
     int dev = 0, sms = 0;
     CBO_CUDA(cudaGetDevice(&dev));
@@ -610,16 +596,15 @@ int obs_gp_fit_impl(const cbo_set_desc* h_sets, int num_sets, double jitter, voi
         for (int p0 = 0; p0 < nb; p0 += W) {
             const int we = nb - p0 < W ? nb - p0 : W;
             for (int q = p0; q < p0 + we; ++q) {
-                if (q > p0) {
-                    chol_colupdate_kernel<<<nb - q, 256, TILE_SMEM, st>>>(A, npad, p0, q);
-                    note_launch();
-                }
+                const size_t ld = npad, step = (size_t)kFB * ld;
+                double* Aq = A + (size_t)q * step;              // block row q
+                if (q > p0)
+                    CBO_CUDA(launch_panel_op(PanelOp{Aq + (size_t)p0 * kFB, Aq + (size_t)p0 * kFB, Aq + (size_t)q * kFB, step, step, ld, ld, ld,
+                                                     (q - p0) * (kFB / kBK), 1, -1}, nb - q, sms, st));
                 potrf_diag_kernel<<<1, 256, DIAG_SMEM, st>>>(A, npad, q, Linv + (size_t)q * kFB * kFB, Wt, info);
                 note_launch();
-                if (nb - q - 1 > 0) {
-                    trsm_panel_kernel<<<nb - q - 1, 256, TILE_SMEM, st>>>(A, npad, q, Linv + (size_t)q * kFB * kFB);
-                    note_launch();
-                }
+                CBO_CUDA(launch_panel_op(PanelOp{Aq + step + (size_t)q * kFB, Linv + (size_t)q * kFB * kFB, Aq + step + (size_t)q * kFB, step, step,
+                                                 ld, (size_t)kFB, ld, kFB / kBK, 0, -1}, nb - q - 1, sms, st));
             }
             const int T = nb - p0 - we;
             if (T > 0) CBO_CUDA(launch_tma_tiles(mapA, mapA, SyrkPlan{A, npad, p0, we, T}, T * (T + 1) / 2, sms, st));
@@ -628,14 +613,12 @@ int obs_gp_fit_impl(const cbo_set_desc* h_sets, int num_sets, double jitter, voi
         for (int K0 = 0; K0 < nb; K0 += W) {
             const int we = nb - K0 < W ? nb - K0 : W;
             for (int K = K0; K < K0 + we; ++K) {
-                if (K > K0) {
-                    winv_colupdate_kernel<<<K, 256, TILE_SMEM, st>>>(A, Wt, npad, K0, K);
-                    note_launch();
-                }
-                if (K > 0) {
-                    winv_scale_kernel<<<K, 256, TILE_SMEM, st>>>(Wt, npad, K, Linv + (size_t)K * kFB * kFB);
-                    note_launch();
-                }
+                const size_t ld = npad, step = (size_t)kFB * ld;
+                if (K > K0)
+                    CBO_CUDA(launch_panel_op(PanelOp{Wt + (size_t)K0 * kFB, A + (size_t)K * step + (size_t)K0 * kFB, Wt + (size_t)K * kFB, step, step,
+                                                     ld, ld, ld, (K - K0) * (kFB / kBK), 1, K0}, K, sms, st));
+                CBO_CUDA(launch_panel_op(PanelOp{Wt + (size_t)K * kFB, Linv + (size_t)K * kFB * kFB, Wt + (size_t)K * kFB, step, step, ld,
+                                                 (size_t)kFB, ld, kFB / kBK, 0, -1}, K, sms, st));
             }
             const int T = nb - K0 - we;
             if (T > 0) CBO_CUDA(launch_tma_tiles(mapW, mapA, WinvPlan{Wt, npad, K0, we, T}, T * (K0 + we), sms, st));
