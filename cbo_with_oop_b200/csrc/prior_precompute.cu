@@ -12,7 +12,7 @@
 //          dmma_tile.cuh (mblk_off) that K1b streams with one TMA bulk copy per pipeline stage.
 // Roofline: FP64 pipe, 2 N^2 S_mc dense-counted flops (N^2 S_mc executed).  No conditioning columns (c == 0)
 // degenerates to M = s2^2 Kyinv.
-#include "dmma_tile.cuh"
+#include "dmma_tma_tile.cuh"
 
 namespace cbo {
 
@@ -121,6 +121,37 @@ syrk_kernel(const double* __restrict__ P, int n_mc_pad, const double* __restrict
         }
     }
 }
+
+// The same product for a set whose block triangle covers the GPU (n_obs_pad (n_obs_pad / 128 + 1) / 256 tiles >= SMs): persistent
+// CTAs on the tensor-map TMA pipeline of dmma_tma_tile.cuh (P is a plain row-major matrix), same epilogue.
+struct PriorSyrkPlan {
+    const double* kyinv;
+    double* M;
+    double coef;
+    int n_obs, n_obs_pad, nT, nk;
+    __device__ int count() const { return nT * (nT + 1) / 2; }
+    __device__ TileJob job(int t) const {
+        int bi, bj;
+        tri_tile(t, bi, bj);
+        return TileJob{bi * CBO_NPAD, bj * CBO_NPAD, 0, nk, bi, bj};
+    }
+    __device__ void store(const TileJob& j, const double (&acc)[8][4][2], int tid) const {
+        const int bi = j.ti, bj = j.tj;
+        tma_for_each_acc(acc, tid, [&](int rr, int cc, double a0, double a1) {
+            const int r = bi * CBO_NPAD + rr, cidx = bj * CBO_NPAD + cc;
+            double v0 = 0.0, v1 = 0.0;
+            if (r < n_obs) {
+                if (cidx < n_obs) v0 = coef * kyinv[(size_t)r * n_obs + cidx] * a0;
+                if (cidx + 1 < n_obs) v1 = coef * kyinv[(size_t)r * n_obs + cidx + 1] * a1;
+            }
+            *reinterpret_cast<double2*>(M + mblk_off(r, cidx, n_obs_pad)) = make_double2(v0, v1);
+            if (bi != bj) {
+                M[mblk_off(cidx, r, n_obs_pad)] = v0;
+                M[mblk_off(cidx + 1, r, n_obs_pad)] = v1;
+            }
+        });
+    }
+};
 
 // ---- batched forms: every set of the call in ONE launch per stage (the reference's shipped sizes are 25 sets of
 // N = 100..200 -- per-set launches cost more than the work).  Needs the descriptors on the device and a private P
@@ -235,6 +266,9 @@ int prior_precompute_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets
     CBO_CUDA(allow_dynamic_smem(kern, SMEM));
     // batched launches need the descriptors on the device and P buffers that no two sets share
     bool batched = d_sets != nullptr && num_sets > 1;
+    int dev = 0, sms = 0;
+    CBO_CUDA(cudaGetDevice(&dev));
+    CBO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     long long tiles_total = 0;
     int npad_max = 0;
     for (int s = 0; s < num_sets; ++s) {
@@ -245,6 +279,7 @@ int prior_precompute_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets
         CBO_REQUIRE(S.P && S.x_obs_cond && S.mc_cond, "cbo_prior_precompute: set %d has a NULL P/x_obs_cond/mc_cond", s);
         const int nT = S.n_obs_pad / CBO_NPAD;
         tiles_total += (long long)nT * (nT + 1) / 2;
+        if (nT * (nT + 1) / 2 >= sms) batched = false;      // a set that fills the GPU on its own takes the TMA pipeline below
         if (S.n_obs_pad > npad_max) npad_max = S.n_obs_pad;
         const double* e0 = S.P + (size_t)S.n_obs_pad * S.n_mc_pad;
         for (int t = 0; t < s && batched; ++t) {
@@ -282,6 +317,13 @@ int prior_precompute_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets
         CBO_CUDA(cudaGetLastError());
         const int nT = S.n_obs_pad / CBO_NPAD;
         const int tiles = nT * (nT + 1) / 2;
+        if (tiles >= sms) {
+            CUtensorMap mapP;
+            if (make_f64_rowmajor_map(&mapP, S.P, S.n_obs_pad, S.n_mc_pad, S.n_mc_pad)) return -1;
+            CBO_CUDA(launch_tma_tiles(mapP, mapP, PriorSyrkPlan{S.kyinv, S.M, (S.s2 * S.s2) / (double)S.n_mc, S.n_obs, S.n_obs_pad, nT,
+                                                               S.n_mc_pad / kBK}, tiles, sms, st));
+            continue;
+        }
         kern<<<tiles, 256, SMEM, st>>>(S.P, S.n_mc_pad, S.kyinv, S.n_obs, S.n_obs_pad, (S.s2 * S.s2) / (double)S.n_mc, S.M);
         note_launch();
         CBO_CUDA(cudaGetLastError());

@@ -225,3 +225,21 @@ def test_combine_kernel_matches_rule(cuda_engine_ready):
         assert sb[s].n_nan == sum(range(R))
     assert res.set == 0 and res.value == 5.0
     assert res.n_nan == (S) * sum(range(R))
+
+
+@pytest.mark.parametrize("S_mc", [40, 333])
+def test_prior_precompute_of_a_set_that_fills_the_gpu(cuda_engine_ready, S_mc):
+    """N = 2200 (18 row blocks, 171 lower-triangle tiles >= the 148 SMs): K1a's SYRK takes the persistent tensor-map TMA
+    pipeline (dmma_tma_tile.cuh) instead of the one-tile-per-CTA kernel.  S_mc = 40 is a product of 3 slabs -- shorter
+    than the 6-stage ring -- and 333 wraps it several times.  M, w and the prior at the interventional rows against the oracle."""
+    kw, ora = make_case(seed=41, N=2200, d=1, c=2, n=6, p=(50,), S_mc=S_mc)
+    eng = _engine([kw])
+    best = float(np.min(kw["y_int"]))
+    out = eng.sweep(best, "min")
+    ref = oracle_sweep(ora, best, "min")
+    f = O.prior_factors(ora["gp"], ora["cond"], ora["cols"])
+    assert rel_err(eng.fetch("M", 0), f["M"], 1e-6 * np.abs(f["M"]).max()).max() <= RTOL
+    assert rel_err(eng.fetch("w", 0), f["w"], 1e-6 * np.abs(f["w"]).max()).max() <= RTOL
+    assert rel_err(eng.fetch("m", 0), ref["mg"], 1e-6).max() <= RTOL
+    assert rel_err(eng.fetch("v", 0), ref["vg"], 1e-6).max() <= RTOL
+    assert out.index == ref["idx"]
