@@ -21,11 +21,26 @@ best = best_of(probs)
 eng.sweep(best, "min")
 rng = np.random.default_rng(0)
 x, y = probs[0].x_int.copy(), probs[0].y_int.copy()
-ms = []
+ms, host = [], []
+import time
+fin = eng._finish
+marks = {}
+def timed_finish(ev):
+    marks["launched"] = time.perf_counter()
+    return fin(ev)
+eng._finish = timed_finish
 for t in range(args.trials):
     x = np.vstack([x, rng.uniform(-2, 2, (1, len(args.p)))]); y = np.append(y, 0.0)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); eng.set_interventional(0, x, y); out = eng.refresh(best, "min", refit=[0]); e1.record(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0.record(); eng.set_interventional(0, x, y)
+    t1 = time.perf_counter()
+    out = eng.refresh(best, "min", refit=[0])
+    t2 = time.perf_counter()
+    e1.record(); torch.cuda.synchronize()
     ms.append(e0.elapsed_time(e1))
-print(json.dumps({"n_obs": args.n_obs, "p": args.p, "ms_per_post_intervention_trial": ms, "selected": [out.set, out.index]}))
+    # host timeline of the trial in microseconds: data upload, Python + library call up to the last launch, wait for the result
+    host.append({"set_interventional_us": (t1 - t0) * 1e6, "refresh_until_launched_us": (marks["launched"] - t1) * 1e6,
+                 "finish_wait_us": (t2 - marks["launched"]) * 1e6})
+print(json.dumps({"n_obs": args.n_obs, "p": args.p, "ms_per_post_intervention_trial": ms, "host_timeline": host, "selected": [out.set, out.index]}))
