@@ -43,6 +43,12 @@ __host__ __device__ inline long long host_items(const cbo_set_desc& S, int /*kin
     return (S.g_count + CBO_SWEEP_TILE - 1) / CBO_SWEEP_TILE;
 }
 
+// K3 evaluates |L^-1 k*|^2 three ways, chosen by the set's own n_int (so a set's arithmetic never depends on which sets
+// share the call): n <= kSweepFmaMaxN forward substitution in registers; n <= kSweepMmaMaxN a DMMA product with L^-1 (K2
+// leaves L^-T in the strict upper triangle of `L` for these sets); beyond that forward substitution in shared memory.
+constexpr int kSweepFmaMaxN = 16;
+constexpr int kSweepMmaMaxN = 48;
+
 // Opt a kernel into `bytes` of dynamic shared memory.  Called before every launch that needs more than 48 KB: the
 // attribute is per device and per context, the call costs about a microsecond, and keeping no "already configured" flag
 // keeps the library free of hidden state (several devices or threads in one process stay correct).

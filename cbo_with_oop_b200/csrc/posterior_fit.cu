@@ -6,6 +6,7 @@
 //                resid = y - m(X)                              (Mapping.f = mean function, :65-68)
 //   non-causal : K = exp(-.5 r^2), resid = y                   (:57-60)
 //   Ky = K + (1e-10 + 1e-8) I ; L = jitchol(Ky) ; alpha = Ky^-1 resid
+// Output `L`: the factor in the lower triangle; for n <= 48 the strict upper triangle carries L^-T (for K3), else zeros.
 // jitchol rule (GPy util.linalg): plain Cholesky first; on a non-positive pivot retry with
 // jitter = mean(diag Ky) * 1e-6 * 10^t, t = 0..4; give up after 5 retries (fit_info[1] = 1, outputs NaN).
 // n <= 128, so the matrix (<= 128 KB) lives in shared memory; latency-bound by construction (n is tiny),
@@ -106,10 +107,31 @@ posterior_fit_kernel(const cbo_set_desc* __restrict__ sets) {
             __syncthreads();
         }
     }
+    // n <= kSweepMmaMaxN: L^-T goes into the strict upper triangle (the diagonal of L^-1 is 1 / L_ii).  K3's tensor-pipe path
+    // multiplies k* by L^-1 (a GEMM over candidates) instead of substituting per candidate.  Thread c owns column c of
+    // W = L^-1, stored as row c of the upper triangle: W[i][c] = -(sum_{c <= j < i} L[i][j] W[j][c]) / L[i][i].
+    const bool with_inv = n <= kSweepMmaMaxN;
+    if (!bad && with_inv) {
+        if (tid < n) {
+            const int c = tid;
+            const double wcc = 1.0 / A[c * n + c];
+            for (int i = c + 1; i < n; ++i) {
+                double a0 = A[i * n + c] * wcc, a1 = 0.0;
+                int j = c + 1;
+                for (; j + 1 < i; j += 2) {
+                    a0 = fma(A[i * n + j], A[c * n + j], a0);
+                    a1 = fma(A[i * n + j + 1], A[c * n + j + 1], a1);
+                }
+                if (j < i) a0 = fma(A[i * n + j], A[c * n + j], a0);
+                A[c * n + i] = -(a0 + a1) / A[i * n + i];
+            }
+        }
+        __syncthreads();
+    }
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
     for (int e = tid; e < n * n; e += kFitThreads) {
         const int i = e / n, j = e % n;
-        S.L[e] = bad ? nan : (j <= i ? A[e] : 0.0);
+        S.L[e] = bad ? nan : ((j <= i || with_inv) ? A[e] : 0.0);
     }
     for (int i = tid; i < n; i += kFitThreads) {
         S.alpha[i] = bad ? nan : rhs[i];

@@ -93,6 +93,20 @@ __host__ __device__ inline bool sweep_separable(const cbo_set_desc& S) {
 }
 __host__ __device__ inline int sweep_lead_rows(const cbo_set_desc& S) { return CBO_SWEEP_TILE / S.p[S.d - 1] + 2; }
 
+// Which launch evaluates a set (decided by the set alone, never by its neighbours in the call):
+//   0  sweep_kernel<16, false>   cached posterior (EI refresh only), or n <= 16 without separable tables
+//   1  sweep_kernel<16, true>    n <= 16 on a tensor grid
+//   2  sweep_mma_kernel<true>    16 < n <= 48 on a tensor grid      (|L^-1 k*|^2 on the FP64 tensor pipe)
+//   3  sweep_mma_kernel<false>   16 < n <= 48, explicit points / very short or long last dimension
+//   4  sweep_kernel<0, false>    n > 48
+enum { kClsFma = 0, kClsFmaSep = 1, kClsMmaSep = 2, kClsMma = 3, kClsGeneric = 4, kNumSweepClasses = 5 };
+__host__ __device__ inline int sweep_class(const cbo_set_desc& S) {
+    if (S.posterior_cached) return kClsFma;
+    if (S.n_int <= kSweepFmaMaxN) return sweep_separable(S) ? kClsFmaSep : kClsFma;
+    if (S.n_int <= kSweepMmaMaxN) return sweep_separable(S) ? kClsMmaSep : kClsMma;
+    return kClsGeneric;
+}
+
 template <int NREG>
 __device__ __forceinline__ void posterior_sep(const SweepSmem& sm, int n, const double* __restrict__ eLast, int ldl,
                                               const double* __restrict__ eLead, int ldr, double svg, double& mu, double& ss) {
@@ -118,15 +132,13 @@ __device__ __forceinline__ void posterior_sep(const SweepSmem& sm, int n, const 
     }
 }
 
-// NREG: register budget of the forward substitution, picked per LAUNCH from the largest n_int of the call (16 / 32 / 48
-// solution entries in registers; 0: any n, the vector lives in shared memory).  One instantiation per launch keeps the
-// small-n kernel (the reference's n = 10 .. ~50) at a register count that lets many CTAs share an SM.
-// SEP: the launch handles the sets whose posterior is evaluated through the separable k* tables (sweep_separable, not
-// posterior_cached); the SEP = false launch handles every other set.  A set's arithmetic therefore never depends on which
-// other sets share the call (ranks that hold different subsets must produce the same bits), and each instantiation
-// carries one path only (half the code, fewer live registers).
+// NREG = 16: n <= 16, the forward substitution runs in registers; NREG = 0: n > 48, the solution vector lives in shared
+// memory (16 < n <= 48 is sweep_mma_kernel's).  SEP: the sets whose posterior is evaluated through the separable k* tables.
+// Which launch takes a set is decided by the set alone (sweep_class), so a set's arithmetic never depends on which other sets
+// share the call (ranks that hold different subsets must produce the same bits), and each instantiation carries one path
+// only (less code, fewer live registers).
 template <int NREG, bool SEP>
-__global__ void __launch_bounds__(kSweepThreads, NREG == 16 ? 5 : (NREG == 0 ? 5 : 3))
+__global__ void __launch_bounds__(kSweepThreads, 5)
 sweep_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, double best, double task_sign,
              cbo_set_best* __restrict__ tile_best) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -136,7 +148,7 @@ sweep_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, double best, d
     const int n = S.n_int, d = S.d, tid = threadIdx.x;
     const bool causal = S.causal != 0;
     const bool cached = S.posterior_cached != 0;   // mu / var of an earlier sweep are still valid: EI refresh only
-    if ((!cached && sweep_separable(S)) != SEP) return;       // the other launch's set
+    if (sweep_class(S) != (NREG == 0 ? kClsGeneric : (SEP ? kClsFmaSep : kClsFma))) return;       // another launch's set
     const bool sep = SEP;
     const int p_last = S.points ? 1 : S.p[d - 1];
 
@@ -283,6 +295,264 @@ sweep_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, double best, d
     }
 }
 
+// ---- 16 < n <= 48: |L^-1 k*|^2 on the FP64 tensor pipe --------------------------------------------------------------------
+// The forward substitution costs n^2/2 FMAs per candidate with one broadcast LDS each: at n = 45 the LSU, not the FP64 pipe,
+// set the pace (ncu, profiles/r02_k3_sweep_refresh_*: FP64 pipe 29 %, LSU wavefronts 33 %, 3 warps per scheduler waiting on
+// each other's loads).  Here t = W k*, W = L^-1 (K2 leaves L^-T in the upper triangle of `L`), is a GEMM over candidates on
+// DMMA.8x8x4: a warp takes 32 consecutive candidates as four groups of 8 rows; per group the A fragments are the candidate's
+// k* values (lane (r, q) evaluates k*_j for j = 4 ks + q: two table loads and one FMA on a tensor grid), the B fragments are
+// the 8 x 4 blocks of W on and below the diagonal, staged once per item in fragment order (conflict-free LDS.64, one per TWO
+// DMMAs: two groups share each load), and the accumulators are t itself: ss = sum of squares, reduced over the 4 lanes of a
+// row; mu = k*.alpha rides along as 12 FMAs.  42 DMMAs per 8 candidates at n = 48 (36.75 if the triangle were cut exactly).
+// Lane 4 r + q then finishes candidate 8 q + r of the warp's 32 (EI, cost, argmax): the group results it needs are already
+// in its own registers.  L^-1 k* has the forward error of a triangular solve with the same factor (n eps |W| |k*|); on the
+// shipped data the variance moves by <= 5e-9 of its parity floor against substitution (measured in NumPy on the golden
+// fixtures).
+constexpr int kMmaNB = kSweepMmaMaxN / 8;             // 8-row output blocks of t
+constexpr int kMmaKS = kSweepMmaMaxN / 4;             // k4 steps
+constexpr int kMmaSlots = kMmaNB * (kMmaNB + 1);      // fragments of W's block lower triangle: block ib has 2 ib + 2 of them
+__host__ __device__ inline int sweep_mma_lead_rows(int p_last, int chunk) { return chunk * CBO_SWEEP_TILE / p_last + 2; }
+constexpr int kMmaMaxChunk = 64;                      // <= kMmaThreads (one thread per neutral slot), bounds the lead-row table
+__host__ __device__ inline int sweep_mma_ldl(int p_last) { return ((p_last + 3) / 8) * 8 + 4; }   // = 4 (mod 8): 4 rows x 4 columns of a half-warp hit 16 banks
+
+constexpr int kMmaThreads = 512;                     // 16 warps, one CTA per SM: an item is two rounds of 16 warp passes
+template <bool SEP>
+__global__ void __launch_bounds__(kMmaThreads, 1)
+sweep_mma_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, double best, double task_sign,
+                 cbo_set_best* __restrict__ tile_best, int chunk) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int tile;
+    const int s = find_item(sets, num_sets, kItemsSweep, blockIdx.x, tile);
+    const cbo_set_desc& S = sets[s];
+    if (sweep_class(S) != (SEP ? kClsMmaSep : kClsMma)) return;       // another launch's set
+    // `chunk` consecutive items of a set are swept by the CTA of the first one: the per-item staging (n (p_last + rows) exp for
+    // the k* tables, the fragments of L^-1) was 14 % of the kernel with one item per CTA, and a launch of few long-lived CTAs
+    // has no wave quantisation.  The chunk's argmax goes to its first item's slot, the other slots get the neutral element.
+    if (tile % chunk != 0) return;
+    const int n = S.n_int, d = S.d, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r = lane >> 2, q = lane & 3;
+    const bool causal = S.causal != 0;
+    const int p_last = S.points ? 1 : S.p[d - 1];
+    const int nb = (n + 7) >> 3, ksn = (n + 3) >> 2;
+
+    double* Wf = reinterpret_cast<double*>(smem_raw);          // [slot][lane]
+    double* al = Wf + kMmaSlots * 32;
+    double* sv = al + kSweepMmaMaxN;
+    double* xs = sv + kSweepMmaMaxN;                            // n x d
+    double* eLast = xs + kSweepMmaMaxN * CBO_MAX_D;             // [n][ldl]
+    const int ldl = sweep_mma_ldl(p_last), ldr = sweep_mma_lead_rows(p_last, chunk) | 1;
+    double* eLead = eLast + (size_t)n * ldl;                    // [n][ldr]
+    __shared__ double red_v[kMmaThreads / 32];
+    __shared__ long long red_i[kMmaThreads / 32];
+    __shared__ int red_n[kMmaThreads / 32];
+
+    const long long loc0 = (long long)tile * CBO_SWEEP_TILE;
+    const long long left = S.g_count - loc0;
+    const int cnt = left < (long long)chunk * CBO_SWEEP_TILE ? (int)left : chunk * CBO_SWEEP_TILE;
+    const long long gidx0 = S.g_begin + loc0;
+    const long long row_first = S.points ? gidx0 : gidx0 / p_last;
+    const int off0 = S.points ? 0 : (int)(gidx0 - row_first * p_last);
+
+    for (int e = tid; e < nb * (nb + 1) * 32; e += kMmaThreads) {
+        const int slot = e >> 5, l = e & 31;
+        int ib = 0;
+        while ((ib + 1) * (ib + 2) <= slot) ++ib;
+        const int i = 8 * ib + (l >> 2), j = 4 * (slot - ib * (ib + 1)) + (l & 3);
+        double w = 0.0;
+        if (i < n && j <= i) w = (j == i) ? 1.0 / S.L[(size_t)i * n + i] : S.L[(size_t)j * n + i];
+        Wf[e] = w;
+    }
+    for (int i = tid; i < n; i += kMmaThreads) {
+        al[i] = S.alpha[i];
+        sv[i] = causal ? S.sqrt_v_int[i] : 0.0;
+    }
+    for (int i = tid; i < n * d; i += kMmaThreads) xs[i] = S.x_int[i];
+    if (SEP) {
+        const double* __restrict__ gl = S.grid[d - 1];
+        for (int e = tid; e < n * p_last; e += kMmaThreads) {
+            const int i = e / p_last, j = e - i * p_last;
+            const double t = gl[j] - S.x_int[i * d + d - 1];
+            eLast[i * ldl + j] = exp(-0.5 * (t * t));
+        }
+        const long long last_row = (gidx0 + cnt - 1) / p_last;
+        const int nrows = (int)(last_row - row_first) + 1;
+        for (int e = tid; e < n * nrows; e += kMmaThreads) {
+            const int i = e / nrows, rw = e - i * nrows;
+            long long rr = row_first + rw;
+            double r2 = 0.0;
+            for (int k = d - 2; k >= 0; --k) {
+                const long long pk = S.p[k];
+                const double t = S.grid[k][(int)(rr % pk)] - S.x_int[i * d + k];
+                r2 = fma(t, t, r2);
+                rr /= pk;
+            }
+            eLead[i * ldr + rw] = exp(-0.5 * r2);
+        }
+    }
+    __syncthreads();
+
+    double val = -DBL_MAX * 2.0;  // -inf
+    long long idx = LLONG_MAX;
+    int n_nan = 0;
+#pragma unroll 1
+    for (int c0 = warp * 32; c0 < cnt; c0 += kMmaThreads) {
+        // this lane's own candidate (the one it finishes): 8 q + r of the warp's 32; a dead tail lane shadows the last live one
+        const int c_own = c0 + 8 * q + r;
+        const bool live = c_own < cnt;
+        const int c = live ? c_own : cnt - 1;
+        const long long loc = loc0 + c, gidx = gidx0 + c;
+        const double vg = causal ? S.v[loc] : 0.0;
+        const double mg = causal ? S.m[loc] : 0.0;
+        const double svg = causal ? sqrt(vg) : 0.0;
+        int lrow = 0, jj = 0;
+        double x[CBO_MAX_D];
+#pragma unroll
+        for (int k = 0; k < CBO_MAX_D; ++k) x[k] = 0.0;
+        if (!S.points) {
+            const unsigned off = (unsigned)(off0 + c);
+            lrow = (int)(off / (unsigned)p_last);
+            jj = (int)(off - (unsigned)lrow * (unsigned)p_last);
+        }
+        if (!SEP || S.cost_variable) {
+            if (S.points) {
+#pragma unroll
+                for (int k = 0; k < CBO_MAX_D; ++k) x[k] = k < d ? S.points[gidx * d + k] : 0.0;
+            } else {
+                long long rr = row_first + lrow;
+                x[d - 1] = S.grid[d - 1][jj];
+                for (int k = d - 2; k >= 0; --k) {
+                    const long long pk = S.p[k];
+                    x[k] = S.grid[k][(int)(rr % pk)];
+                    rr /= pk;
+                }
+            }
+        }
+        double mu = 0.0, ss = 0.0;
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g) {
+            double a[kMmaKS], acc[kMmaNB][2];
+            const int src = (lane & ~3) | g;      // the lane that owns candidate 8 g + r
+            const double svg_g = __shfl_sync(0xffffffffu, svg, src);
+            double mp = 0.0;
+            if (SEP) {
+                const double* __restrict__ eR = eLead + __shfl_sync(0xffffffffu, lrow, src);
+                const double* __restrict__ eL = eLast + __shfl_sync(0xffffffffu, jj, src);
+#pragma unroll
+                for (int ks = 0; ks < kMmaKS; ++ks) {
+                    a[ks] = 0.0;
+                    if (ks < ksn) {
+                        const int j = 4 * ks + q, jc = j < n ? j : n - 1;
+                        const double kv = fma(eR[jc * ldr], eL[jc * ldl], sv[jc] * svg_g);
+                        a[ks] = j < n ? kv : 0.0;
+                        mp = fma(a[ks], al[jc], mp);
+                    }
+                }
+            } else {
+                double xg[CBO_MAX_D];
+#pragma unroll
+                for (int k = 0; k < CBO_MAX_D; ++k) xg[k] = __shfl_sync(0xffffffffu, x[k], src);
+#pragma unroll
+                for (int ks = 0; ks < kMmaKS; ++ks) {
+                    a[ks] = 0.0;
+                    if (ks < ksn) {
+                        const int j = 4 * ks + q, jc = j < n ? j : n - 1;
+                        double r2 = 0.0;
+#pragma unroll
+                        for (int k = 0; k < CBO_MAX_D; ++k) {
+                            if (k < d) { const double t = xg[k] - xs[jc * d + k]; r2 = fma(t, t, r2); }
+                        }
+                        const double kv = exp(-0.5 * r2) + sv[jc] * svg_g;
+                        a[ks] = j < n ? kv : 0.0;
+                        mp = fma(a[ks], al[jc], mp);
+                    }
+                }
+            }
+            double sp = 0.0;
+#pragma unroll
+            for (int ib = 0; ib < kMmaNB; ++ib) acc[ib][0] = acc[ib][1] = 0.0;
+            // k4 step outermost: consecutive DMMAs go to different accumulators (issued block by block they formed dependent
+            // chains of up to 12 and the warp waited out the pipe latency 42 times per group: DMMA pipe 38 % active)
+            // (the B fragments of step ks + 1 are loaded before the DMMAs of step ks are issued)
+            double bn[kMmaNB];
+#pragma unroll
+            for (int ib = 0; ib < kMmaNB; ++ib) bn[ib] = ib < nb ? Wf[(ib * (ib + 1)) * 32 + lane] : 0.0;
+#pragma unroll
+            for (int ks = 0; ks < kMmaKS; ++ks) {
+                if (ks < ksn) {
+                    double bc[kMmaNB];
+#pragma unroll
+                    for (int ib = 0; ib < kMmaNB; ++ib) bc[ib] = bn[ib];
+                    if (ks + 1 < ksn) {
+#pragma unroll
+                        for (int ib = (ks + 1) >> 1; ib < kMmaNB; ++ib)
+                            if (ib < nb) bn[ib] = Wf[(ib * (ib + 1) + ks + 1) * 32 + lane];
+                    }
+#pragma unroll
+                    for (int ib = ks >> 1; ib < kMmaNB; ++ib)
+                        if (ib < nb) dmma884(acc[ib][0], acc[ib][1], a[ks], bc[ib]);
+                }
+            }
+#pragma unroll
+            for (int ib = 0; ib < kMmaNB; ++ib) sp = fma(acc[ib][0], acc[ib][0], fma(acc[ib][1], acc[ib][1], sp));
+            mp += __shfl_xor_sync(0xffffffffu, mp, 1);
+            sp += __shfl_xor_sync(0xffffffffu, sp, 1);
+            mp += __shfl_xor_sync(0xffffffffu, mp, 2);
+            sp += __shfl_xor_sync(0xffffffffu, sp, 2);
+            if (q == g) { mu = mp; ss = sp; }
+        }
+        mu += mg;
+        const double var = ((1.0 + vg) - ss) + 1e-10;
+        if (live) {
+            if (S.mu) S.mu[loc] = mu;
+            if (S.var) S.var[loc] = var;
+        }
+        const double sd = sqrt(var);
+        const double u = (best - mu) / sd;
+        const double pdf = 0.3989422804014326779 * exp(-0.5 * u * u);
+        const double cdf = 0.5 * erfc(-u * 0.7071067811865475244);
+        const double ei = task_sign * (sd * (u * cdf + pdf));
+        double cost = S.cost_fix;
+        if (S.cost_variable) {
+#pragma unroll
+            for (int k = 0; k < CBO_MAX_D; ++k)
+                if (k < d) cost += fabs(x[k]);
+        }
+        const double acq = ei / cost;
+        if (live) {
+            if (S.ei) S.ei[loc] = ei;
+            if (S.acq) S.acq[loc] = acq;
+            if (acq != acq) ++n_nan;
+            else if (better(acq, gidx, val, idx)) { val = acq; idx = gidx; }
+        }
+    }
+    // first-argmax over the tile
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, val, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        n_nan += __shfl_xor_sync(0xffffffffu, n_nan, o);
+        if (better(ov, oi, val, idx)) { val = ov; idx = oi; }
+    }
+    if (lane == 0) { red_v[warp] = val; red_i[warp] = idx; red_n[warp] = n_nan; }
+    __syncthreads();
+    if (tid == 0) {
+        int nan_total = red_n[0];
+        for (int w = 1; w < kMmaThreads / 32; ++w) {
+            if (better(red_v[w], red_i[w], val, idx)) { val = red_v[w]; idx = red_i[w]; }
+            nan_total += red_n[w];
+        }
+        cbo_set_best b;
+        b.value = val; b.index = idx; b.n_nan = nan_total; b.reserved = 0;
+        tile_best[blockIdx.x] = b;
+    }
+    const int items_here = (cnt + CBO_SWEEP_TILE - 1) / CBO_SWEEP_TILE;
+    if (tid > 0 && tid < items_here) {
+        cbo_set_best b;
+        b.value = -DBL_MAX * 2.0; b.index = LLONG_MAX; b.n_nan = 0; b.reserved = 0;
+        tile_best[blockIdx.x + tid] = b;
+    }
+}
+
 // per-set reduction over the set's tiles (one CTA per set, fixed order)
 __global__ void __launch_bounds__(256)
 set_reduce_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, const cbo_set_best* __restrict__ tile_best,
@@ -360,9 +630,10 @@ int sweep_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_s
     CBO_REQUIRE(task_sign == 1 || task_sign == -1, "cbo_sweep: task_sign must be +1 ('min') or -1 ('max')");
     CBO_REQUIRE(d_tile_best && d_set_best && d_result, "cbo_sweep: NULL output pointer");
     long long total = 0;
-    int nmax = 1;
-    bool any_sep = false, any_gen = false;   // sets for the separable-table launch / for the general launch
-    size_t tab_doubles = 0;      // the two k* tables of the separable path, or the generic path's [n][threads] workspace
+    // per launch class (sweep_class): is there a set for it, its largest n_int, and its k* tables / workspace in doubles
+    bool any[kNumSweepClasses] = {false, false, false, false, false};
+    int nmax[kNumSweepClasses] = {1, 1, 1, 1, 1};
+    size_t tab[kNumSweepClasses] = {0, 0, 0, 0, 0};
     for (int s = 0; s < num_sets; ++s) {
         const cbo_set_desc& S = h_sets[s];
         CBO_REQUIRE(S.n_int >= 1 && S.n_int <= CBO_MAX_NINT, "cbo_sweep: set %d n_int=%d outside [1,%d]", s, S.n_int, CBO_MAX_NINT);
@@ -371,39 +642,58 @@ int sweep_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_s
         CBO_REQUIRE(!S.causal || (S.m && S.v && S.sqrt_v_int), "cbo_sweep: causal set %d needs m/v/sqrt_v_int", s);
         for (int k = 0; k < (S.points ? 0 : S.d); ++k) CBO_REQUIRE(S.grid[k], "cbo_sweep: set %d grid[%d] is NULL", s, k);
         total += host_items(S, kItemsSweep);
-        if (S.n_int > nmax) nmax = S.n_int;
+        if (S.g_count <= 0) continue;
+        const int c = sweep_class(S);
+        any[c] = true;
+        if (!S.posterior_cached && S.n_int > nmax[c]) nmax[c] = S.n_int;
         size_t t = 0;
-        if (S.g_count > 0) {
-            if (!S.posterior_cached && sweep_separable(S)) {
-                t = (size_t)S.n_int * ((S.p[S.d - 1] | 1) + (sweep_lead_rows(S) | 1));
-                any_sep = true;
-            } else {
-                any_gen = true;
-            }
-        }
-        if (t > tab_doubles) tab_doubles = t;
+        if (c == kClsFmaSep) t = (size_t)S.n_int * ((S.p[S.d - 1] | 1) + (sweep_lead_rows(S) | 1));
+        if (c == kClsGeneric) t = (size_t)S.n_int * kSweepThreads;
+        if (t > tab[c]) tab[c] = t;
     }
     CBO_REQUIRE(total < 2147483647LL, "cbo_sweep: too many work items");
+    // chunk length of the tensor-pipe launch: its items spread once over the SMs, within the shared memory the longest
+    // lead-row table needs
+    int chunk = 1;
+    const size_t mma_base = ((size_t)kMmaSlots * 32 + 2 * kSweepMmaMaxN + (size_t)kSweepMmaMaxN * CBO_MAX_D) * sizeof(double);
+    if (any[kClsMmaSep]) {
+        int dev = 0, sms = 0;
+        CBO_CUDA(cudaGetDevice(&dev));
+        CBO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        long long items = 0;
+        for (int s = 0; s < num_sets; ++s)
+            if (h_sets[s].g_count > 0 && sweep_class(h_sets[s]) == kClsMmaSep) items += host_items(h_sets[s], kItemsSweep);
+        chunk = (int)((items + sms - 1) / sms);
+        if (chunk > kMmaMaxChunk) chunk = kMmaMaxChunk;
+        for (;; --chunk) {
+            tab[kClsMmaSep] = 0;
+            for (int s = 0; s < num_sets; ++s) {
+                const cbo_set_desc& S = h_sets[s];
+                if (S.g_count <= 0 || sweep_class(S) != kClsMmaSep) continue;
+                const int pl = S.p[S.d - 1];
+                const size_t t = (size_t)S.n_int * (sweep_mma_ldl(pl) + (sweep_mma_lead_rows(pl, chunk) | 1));
+                if (t > tab[kClsMmaSep]) tab[kClsMmaSep] = t;
+            }
+            if (chunk == 1 || mma_base + tab[kClsMmaSep] * sizeof(double) <= 160 * 1024) break;
+        }
+    }
     if (total > 0) {
-        // sets with n_int > 48 are not separable (sweep_separable), so the table launch never needs the generic workspace
-        const size_t base = ((size_t)nmax * (nmax + 1) / 2 + 2 * (size_t)nmax + (size_t)nmax * CBO_MAX_D) * sizeof(double);
-        if (any_sep) {
-            const size_t smem = base + tab_doubles * sizeof(double);
-            auto kern = nmax <= 16 ? sweep_kernel<16, true> : (nmax <= 32 ? sweep_kernel<32, true> : sweep_kernel<48, true>);
-            if (smem > 48 * 1024) CBO_CUDA(allow_dynamic_smem(kern, smem));
-            kern<<<(unsigned)total, kSweepThreads, smem, st>>>(d_sets, num_sets, best, (double)task_sign, d_tile_best);
-            note_launch();
-            CBO_CUDA(cudaGetLastError());
-        }
-        if (any_gen) {
-            const size_t smem = base + (nmax > 48 ? (size_t)nmax * kSweepThreads * sizeof(double) : 0);
-            auto kern = nmax <= 16 ? sweep_kernel<16, false> : (nmax <= 32 ? sweep_kernel<32, false> :
-                        (nmax <= 48 ? sweep_kernel<48, false> : sweep_kernel<0, false>));
-            if (smem > 48 * 1024) CBO_CUDA(allow_dynamic_smem(kern, smem));
-            kern<<<(unsigned)total, kSweepThreads, smem, st>>>(d_sets, num_sets, best, (double)task_sign, d_tile_best);
-            note_launch();
-            CBO_CUDA(cudaGetLastError());
-        }
+        auto fma_smem = [&](int c) {
+            return ((size_t)nmax[c] * (nmax[c] + 1) / 2 + 2 * (size_t)nmax[c] + (size_t)nmax[c] * CBO_MAX_D + tab[c]) * sizeof(double);
+        };
+#define CBO_SWEEP_LAUNCH(kern, threads, smem, ...)                                                                           \
+    do {                                                                                                       \
+        if ((smem) > 48 * 1024) CBO_CUDA(allow_dynamic_smem(kern, (smem)));                                    \
+        kern<<<(unsigned)total, (threads), (smem), st>>>(d_sets, num_sets, best, (double)task_sign, d_tile_best __VA_ARGS__); \
+        note_launch();                                                                                         \
+        CBO_CUDA(cudaGetLastError());                                                                          \
+    } while (0)
+        if (any[kClsFmaSep]) CBO_SWEEP_LAUNCH((sweep_kernel<16, true>), kSweepThreads, fma_smem(kClsFmaSep));
+        if (any[kClsMmaSep]) CBO_SWEEP_LAUNCH((sweep_mma_kernel<true>), kMmaThreads, mma_base + tab[kClsMmaSep] * sizeof(double), , chunk);
+        if (any[kClsFma]) CBO_SWEEP_LAUNCH((sweep_kernel<16, false>), kSweepThreads, fma_smem(kClsFma));
+        if (any[kClsMma]) CBO_SWEEP_LAUNCH((sweep_mma_kernel<false>), kMmaThreads, mma_base, , 1);
+        if (any[kClsGeneric]) CBO_SWEEP_LAUNCH((sweep_kernel<0, false>), kSweepThreads, fma_smem(kClsGeneric));
+#undef CBO_SWEEP_LAUNCH
     }
     set_reduce_kernel<<<num_sets, 256, 0, st>>>(d_sets, num_sets, d_tile_best, d_set_best);
     note_launch();

@@ -643,12 +643,15 @@ class SweepEngine:
         """Device array of global set g as NumPy (parity tests / debugging)."""
         li = self.local_of[g]
         pr, b, D = self.problems[g], self.buf[li], self.h_sets[li]
-        t = b[name].cpu().numpy()
+        t = b["L" if name == "Linv" else name].cpu().numpy()
         n = D.n_int
         if name in ("m", "v", "mu", "var", "ei", "acq"):
             return t[:D.g_count]
-        if name == "L":
-            return t[:n * n].reshape(n, n)
+        if name == "L":      # the factor; for n <= 48 K2 leaves L^-T in the strict upper triangle (K3's tensor-pipe path): "Linv"
+            return np.tril(t[:n * n].reshape(n, n))
+        if name == "Linv":
+            A = t[:n * n].reshape(n, n)
+            return np.triu(A, 1).T + np.diag(1.0 / np.diag(A))
         if name in ("alpha", "sqrt_v_int", "m_int", "v_int", "y_int"):
             return t[:n]
         if name == "x_int":

@@ -80,7 +80,8 @@ typedef struct cbo_set_desc {
     const double* y_int;       /* (n_int) */
     double* m_int;             /* (n_int) prior mean at x_int      [written by cbo_prior_eval which=1] */
     double* v_int;             /* (n_int) prior variance at x_int  */
-    double* L;                 /* (n_int, n_int) row-major lower Cholesky factor [cbo_posterior_fit] */
+    double* L;                 /* (n_int, n_int) row-major lower Cholesky factor [cbo_posterior_fit]; for n_int <= 48 its strict upper
+                                  triangle carries L^-T, which cbo_sweep multiplies by on the FP64 tensor pipe (16 < n_int <= 48) */
     double* alpha;             /* (n_int) Ky^-1 (y - m) */
     double* sqrt_v_int;        /* (n_int) sqrt(v_int) */
     int32_t* fit_info;         /* [0] jitter retries used (0..5), [1] 0 ok / 1 not positive definite */

@@ -55,6 +55,17 @@ CASES = [
     dict(seed=6, N=300, d=3, c=5, n=33, p=(12, 12, 12), S_mc=150),
     dict(seed=7, N=128, d=2, c=0, n=9, p=(31, 5)),
     dict(seed=8, N=100, d=2, c=2, n=10, p=(21, 21), duplicate_train_point=True),
+    # 16 < n <= 48: |L^-1 k*|^2 through the DMMA product with L^-1 (sweep_mma_kernel), separable tables and general form,
+    # partial tiles, n on and off the 8-row block / k4-step boundaries, a candidate on an interventional row
+    dict(seed=61, N=96, d=2, c=1, n=17, p=(40, 45)),
+    dict(seed=62, N=120, d=3, c=2, n=24, p=(20, 20, 37)),
+    dict(seed=63, N=96, d=2, c=2, n=32, p=(50, 101), cost_variable=True),
+    dict(seed=64, N=130, d=3, c=1, n=45, p=(10, 12, 100), duplicate_train_point=True),
+    # (1-D sets this size need room: 48 points inside [-2, 2] give a fit of condition 3e9, where two backward-stable CPU
+    # solvers already differ by 2e-5 in mu)
+    dict(seed=71, N=64, d=1, c=2, n=48, p=(2000,), lo=-60.0, hi=60.0),
+    dict(seed=66, N=64, d=1, c=1, n=41, p=(200,), lo=-30.0, hi=30.0),
+    dict(seed=67, N=80, d=2, c=1, n=30, p=(300, 7), duplicate_train_point=True),
 ]
 
 
@@ -70,6 +81,9 @@ def test_single_set_all_stages(cuda_engine_ready, case, task):
     print(case["seed"], task, {k: (f"{v:.2e}" if isinstance(v, float) else v) for k, v in rep.items()})
     info = eng.fetch("fit_info", 0)
     assert info[1] == 0 and info[0] == ref["tries"]
+    if case["n"] <= 48:     # L^-T in the strict upper triangle of the factor (input of K3's tensor-pipe path)
+        L, W = eng.fetch("L", 0), eng.fetch("Linv", 0)
+        assert np.abs(W @ L - np.eye(case["n"])).max() <= 1e-9 * np.linalg.cond(L)
     for k, v in rep.items():
         if k.endswith("_pts"):
             continue
