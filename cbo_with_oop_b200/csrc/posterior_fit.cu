@@ -27,7 +27,9 @@ posterior_fit_kernel(const cbo_set_desc* __restrict__ sets) {
     double* sv = A + (size_t)n * n;                   // sqrt(v_int)
     double* rhs = sv + n;                             // y - m, then the solution
     double* xs = rhs + n;                             // x_int copy, n x d
-    __shared__ int fail;
+    double* rinv = xs + (size_t)n * CBO_MAX_D;        // 1 / L_ii
+    double* dsq = rinv + n;                           // L_ii
+    bool failed = false;
     __shared__ double diag_mean;
 
     for (int i = tid; i < n; i += kFitThreads) {
@@ -52,7 +54,6 @@ posterior_fit_kernel(const cbo_set_desc* __restrict__ sets) {
             if (i == j) kij += (1e-10 + 1e-8) + jitter;
             A[e] = kij;
         }
-        if (tid == 0) fail = 0;
         __syncthreads();
         if (tries == 0) {  // mean of the diagonal of Ky, the scale of GPy's jitter
             if (tid == 0) {
@@ -62,68 +63,92 @@ posterior_fit_kernel(const cbo_set_desc* __restrict__ sets) {
             }
             __syncthreads();
         }
-        // right-looking Cholesky, lower
+        // Right-looking Cholesky, lower.  Every thread reads the same pivot (so the failure branch is uniform) and forms
+        // 1 / sqrt(pivot) itself; the diagonal is written after the loop (nobody waits for thread 0, two barriers per column
+        // instead of three); the trailing update walks a 16 x 16 thread grid (no integer division per element).  The
+        // arithmetic is LAPACK's: scale the column, then subtract products of scaled entries.
+        failed = false;
         for (int j = 0; j < n; ++j) {
-            if (tid == 0) {
-                const double piv = A[j * n + j];
-                if (!(piv > 0.0)) fail = 1;
-                A[j * n + j] = sqrt(piv);
-            }
-            __syncthreads();
-            if (fail) break;
-            const double inv = 1.0 / A[j * n + j];
+            const double piv = A[j * n + j];
+            if (!(piv > 0.0)) { failed = true; break; }
+            const double sq = sqrt(piv);
+            const double inv = 1.0 / sq;
+            if (tid == 0) dsq[j] = sq;
             for (int i = j + 1 + tid; i < n; i += kFitThreads) A[i * n + j] *= inv;
             __syncthreads();
-            const int rem = n - 1 - j;  // trailing update of the lower triangle
-            for (int e = tid; e < rem * rem; e += kFitThreads) {
-                const int i = j + 1 + e / rem, k = j + 1 + e % rem;
-                if (k <= i) A[i * n + k] -= A[i * n + j] * A[k * n + j];
-            }
+            for (int i = j + 1 + (tid >> 4); i < n; i += kFitThreads / 16)
+                for (int k = j + 1 + (tid & 15); k <= i; k += 16) A[i * n + k] -= A[i * n + j] * A[k * n + j];
             __syncthreads();
         }
-        if (!fail) break;
-        __syncthreads();
+        if (!failed) break;
+        __syncthreads();     // (a thread may still be reading the failing pivot while the next Gram is written)
         if (tries == 5) break;
         jitter = (tries == 0) ? diag_mean * 1e-6 : jitter * 10.0;
         ++tries;
     }
-    const bool bad = fail != 0;
-    __syncthreads();
+    const bool bad = failed;
 
     if (!bad) {
-        // forward L z = rhs, backward L^T a = z (n is tiny: one thread walks the recurrence, the CTA does the updates)
-        for (int j = 0; j < n; ++j) {
-            if (tid == 0) rhs[j] /= A[j * n + j];
-            __syncthreads();
-            const double zj = rhs[j];
-            for (int i = j + 1 + tid; i < n; i += kFitThreads) rhs[i] -= A[i * n + j] * zj;
-            __syncthreads();
+        for (int j = tid; j < n; j += kFitThreads) {
+            A[j * n + j] = dsq[j];
+            rinv[j] = 1.0 / dsq[j];
         }
-        for (int j = n - 1; j >= 0; --j) {
-            if (tid == 0) rhs[j] /= A[j * n + j];
-            __syncthreads();
-            const double aj = rhs[j];
-            for (int i = tid; i < j; i += kFitThreads) rhs[i] -= A[j * n + i] * aj;
-            __syncthreads();
+        __syncthreads();
+        // forward L z = rhs, backward L^T a = z in ONE warp, no CTA barriers: lane l owns rows l, l + 32, l + 64, l + 96 in
+        // registers, the pivot row's value travels by shuffle (two barriers per row and a division by thread 0 before)
+        if (tid < 32) {
+            double z[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) z[r] = (tid + 32 * r < n) ? rhs[tid + 32 * r] : 0.0;
+            for (int j = 0; j < n; ++j) {
+                const int slot = j >> 5;
+                const double own = (slot == 0 ? z[0] : slot == 1 ? z[1] : slot == 2 ? z[2] : z[3]) / dsq[j];
+                const double zj = __shfl_sync(0xffffffffu, own, j & 31);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int i = tid + 32 * r;
+                    if (i == j) z[r] = zj;
+                    else if (i > j && i < n) z[r] = fma(-A[i * n + j], zj, z[r]);
+                }
+            }
+            for (int j = n - 1; j >= 0; --j) {
+                const int slot = j >> 5;
+                const double own = (slot == 0 ? z[0] : slot == 1 ? z[1] : slot == 2 ? z[2] : z[3]) / dsq[j];
+                const double aj = __shfl_sync(0xffffffffu, own, j & 31);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int i = tid + 32 * r;
+                    if (i == j) z[r] = aj;
+                    else if (i < j) z[r] = fma(-A[j * n + i], aj, z[r]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (tid + 32 * r < n) rhs[tid + 32 * r] = z[r];
         }
+        __syncthreads();
     }
     // n <= kSweepMmaMaxN: L^-T goes into the strict upper triangle (the diagonal of L^-1 is 1 / L_ii).  K3's tensor-pipe path
-    // multiplies k* by L^-1 (a GEMM over candidates) instead of substituting per candidate.  Thread c owns column c of
-    // W = L^-1, stored as row c of the upper triangle: W[i][c] = -(sum_{c <= j < i} L[i][j] W[j][c]) / L[i][i].
+    // multiplies k* by L^-1 (a GEMM over candidates) instead of substituting per candidate.  Column c of
+    // W = L^-1 is stored as row c of the upper triangle: W[i][c] = -(sum_{c <= j < i} L[i][j] W[j][c]) / L[i][i].
     const bool with_inv = n <= kSweepMmaMaxN;
     if (!bad && with_inv) {
-        if (tid < n) {
-            const int c = tid;
-            const double wcc = 1.0 / A[c * n + c];
-            for (int i = c + 1; i < n; ++i) {
-                double a0 = A[i * n + c] * wcc, a1 = 0.0;
-                int j = c + 1;
-                for (; j + 1 < i; j += 2) {
-                    a0 = fma(A[i * n + j], A[c * n + j], a0);
-                    a1 = fma(A[i * n + j + 1], A[c * n + j + 1], a1);
+        // four lanes per column split every dot product and combine by a fixed butterfly: 64 columns at once, one round for
+        // n <= 48 (a single thread per column made the inverse a 20 us chain at n = 45).  Lane sub = 0 stores.
+        const int sub = tid & 3;
+        for (int c = tid >> 2; c < ((n + 63) & ~63); c += kFitThreads / 4) {        // warp-uniform trip count
+            const bool col = c < n;
+            const double wcc = col ? rinv[c] : 0.0;
+            for (int i = (c & ~7) + 1; i < n; ++i) {      // row i of column c, i > c (a warp holds columns 8 w .. 8 w + 7)
+                double a0 = 0.0;
+                if (col && i > c) {
+                    for (int j = c + 1 + sub; j < i; j += 4) a0 = fma(A[i * n + j], A[c * n + j], a0);
+                    if (sub == 0) a0 = fma(A[i * n + c], wcc, a0);
                 }
-                if (j < i) a0 = fma(A[i * n + j], A[c * n + j], a0);
-                A[c * n + i] = -(a0 + a1) / A[i * n + i];
+                a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
+                a0 += __shfl_xor_sync(0xffffffffu, a0, 2);
+                if (col && i > c && sub == 0) A[c * n + i] = -a0 * rinv[i];
+                __syncwarp();
             }
         }
         __syncthreads();
@@ -152,7 +177,7 @@ int posterior_fit_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, i
         CBO_REQUIRE(!S.causal || (S.m_int && S.v_int), "cbo_posterior_fit: causal set %d needs m_int/v_int", s);
         if (S.n_int > nmax) nmax = S.n_int;
     }
-    const size_t smem = ((size_t)nmax * nmax + 2 * (size_t)nmax + (size_t)nmax * CBO_MAX_D) * sizeof(double);
+    const size_t smem = ((size_t)nmax * nmax + 4 * (size_t)nmax + (size_t)nmax * CBO_MAX_D) * sizeof(double);
     if (smem > 48 * 1024) CBO_CUDA(allow_dynamic_smem(posterior_fit_kernel, smem));
     posterior_fit_kernel<<<num_sets, kFitThreads, smem, st>>>(d_sets);
     note_launch();

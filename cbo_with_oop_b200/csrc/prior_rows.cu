@@ -200,33 +200,44 @@ prior_rows_kernel(const cbo_set_desc* __restrict__ sets, RowsShape sh, double* _
     }
 }
 
-// one CTA per (set, pass), one warp per row: lane l adds the partials of items l, l + 32, ... (a fixed assignment), then a
-// fixed butterfly combines the 32 lanes -- the order of the additions never depends on scheduling
+// one CTA of 32 warps per (set, pass), 32 / rmax warps per row (1 for a whole set, 8 for the row or two a post-intervention
+// trial appends: with one warp its 1580 partials at N = 1e4 were a 36 us chain of dependent loads): thread t of a row's
+// warps adds the partials of items t, t + T, ... (a fixed assignment), a fixed butterfly combines the lanes and the row's
+// first lane adds its warps' sums in warp order -- the order of the additions never depends on scheduling
 __global__ void __launch_bounds__(32 * kRowsWide)
 prior_rows_finalize_kernel(const cbo_set_desc* __restrict__ sets, RowsShape sh, const double* __restrict__ partials) {
+    __shared__ double warp_sums[kRowsWide][4];
     const int set = blockIdx.x / sh.passes, pass = blockIdx.x % sh.passes;
     const cbo_set_desc& S = sets[set];
-    const int lane = threadIdx.x, row = threadIdx.y;
-    if (!computes_prior(S)) return;
+    const int lane = threadIdx.x, warp = threadIdx.y, wpr = kRowsWide / sh.rmax;     // warps per row
+    const int row = warp / wpr, sub = warp - row * wpr;
+    if (!computes_prior(S)) return;      // CTA-uniform
     const int r = rows_first(S) + pass * sh.rmax + row;
-    if (r >= S.n_int) return;            // warp-uniform
     double qh = 0.0, ql = 0.0, mh = 0.0, ml = 0.0;
     const int nJ = rows_nJ(S);
-    for (int e = lane; e < nJ * sh.chunks; e += 32) {
-        const int I = e / sh.chunks, c = e - I * sh.chunks;
-        if (c * kRowsSlabs >= (I + 1) * (kMBlkRows / kBK)) continue;     // the item does not exist (nothing was written)
-        const double* p = partials + rows_partial_index(sh, set, pass, I, c) + row * kRowsPartial;
-        dd_add(p[0], p[1], qh, ql);
-        dd_add(p[2], p[3], mh, ml);
-    }
+    if (r < S.n_int) {                   // warp-uniform
+        for (int e = sub * 32 + lane; e < nJ * sh.chunks; e += 32 * wpr) {
+            const int I = e / sh.chunks, c = e - I * sh.chunks;
+            if (c * kRowsSlabs >= (I + 1) * (kMBlkRows / kBK)) continue;     // the item does not exist (nothing was written)
+            const double* p = partials + rows_partial_index(sh, set, pass, I, c) + row * kRowsPartial;
+            dd_add(p[0], p[1], qh, ql);
+            dd_add(p[2], p[3], mh, ml);
+        }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double oh = __shfl_xor_sync(0xffffffffu, qh, o), ol = __shfl_xor_sync(0xffffffffu, ql, o);
-        const double ph = __shfl_xor_sync(0xffffffffu, mh, o), pl = __shfl_xor_sync(0xffffffffu, ml, o);
-        dd_add(oh, ol, qh, ql);
-        dd_add(ph, pl, mh, ml);
+        for (int o = 16; o > 0; o >>= 1) {
+            const double oh = __shfl_xor_sync(0xffffffffu, qh, o), ol = __shfl_xor_sync(0xffffffffu, ql, o);
+            const double ph = __shfl_xor_sync(0xffffffffu, mh, o), pl = __shfl_xor_sync(0xffffffffu, ml, o);
+            dd_add(oh, ol, qh, ql);
+            dd_add(ph, pl, mh, ml);
+        }
     }
-    if (lane == 0) {
+    if (lane == 0) { warp_sums[warp][0] = qh; warp_sums[warp][1] = ql; warp_sums[warp][2] = mh; warp_sums[warp][3] = ml; }
+    __syncthreads();
+    if (lane == 0 && sub == 0 && r < S.n_int) {
+        for (int w = 1; w < wpr; ++w) {
+            dd_add(warp_sums[warp + w][0], warp_sums[warp + w][1], qh, ql);
+            dd_add(warp_sums[warp + w][2], warp_sums[warp + w][3], mh, ml);
+        }
         S.m_int[r] = mh + ml;
         S.v_int[r] = ((S.s2 + S.noise) - qh) - ql;
     }
@@ -276,7 +287,7 @@ int prior_rows_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int 
     else prior_rows_kernel<kRowsWide><<<grid, kRowsThreads, kRowsRingBytes, st>>>(d_sets, sh, partials);
     note_launch();
     CBO_CUDA(cudaGetLastError());
-    prior_rows_finalize_kernel<<<num_sets * sh.passes, dim3(32, sh.rmax), 0, st>>>(d_sets, sh, partials);
+    prior_rows_finalize_kernel<<<num_sets * sh.passes, dim3(32, kRowsWide), 0, st>>>(d_sets, sh, partials);
     note_launch();
     CBO_CUDA(cudaGetLastError());
     return 0;

@@ -94,14 +94,15 @@ __host__ __device__ inline bool sweep_separable(const cbo_set_desc& S) {
 __host__ __device__ inline int sweep_lead_rows(const cbo_set_desc& S) { return CBO_SWEEP_TILE / S.p[S.d - 1] + 2; }
 
 // Which launch evaluates a set (decided by the set alone, never by its neighbours in the call):
-//   0  sweep_kernel<16, false>   cached posterior (EI refresh only), or n <= 16 without separable tables
+//   0  sweep_kernel<16, false>   n <= 16 without separable tables; cached posterior with a variable cost
 //   1  sweep_kernel<16, true>    n <= 16 on a tensor grid
 //   2  sweep_mma_kernel<true>    16 < n <= 48 on a tensor grid      (|L^-1 k*|^2 on the FP64 tensor pipe)
 //   3  sweep_mma_kernel<false>   16 < n <= 48, explicit points / very short or long last dimension
 //   4  sweep_kernel<0, false>    n > 48
-enum { kClsFma = 0, kClsFmaSep = 1, kClsMmaSep = 2, kClsMma = 3, kClsGeneric = 4, kNumSweepClasses = 5 };
+//   5  ei_refresh_kernel         cached posterior, fixed cost: EI refresh from mu / var (16 B per candidate)
+enum { kClsFma = 0, kClsFmaSep = 1, kClsMmaSep = 2, kClsMma = 3, kClsGeneric = 4, kClsCached = 5, kNumSweepClasses = 6 };
 __host__ __device__ inline int sweep_class(const cbo_set_desc& S) {
-    if (S.posterior_cached) return kClsFma;
+    if (S.posterior_cached) return S.cost_variable ? kClsFma : kClsCached;
     if (S.n_int <= kSweepFmaMaxN) return sweep_separable(S) ? kClsFmaSep : kClsFma;
     if (S.n_int <= kSweepMmaMaxN) return sweep_separable(S) ? kClsMmaSep : kClsMma;
     return kClsGeneric;
@@ -341,7 +342,8 @@ sweep_mma_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, double bes
     double* xs = sv + kSweepMmaMaxN;                            // n x d
     double* eLast = xs + kSweepMmaMaxN * CBO_MAX_D;             // [n][ldl]
     const int ldl = sweep_mma_ldl(p_last), ldr = sweep_mma_lead_rows(p_last, chunk) | 1;
-    double* eLead = eLast + (size_t)n * ldl;                    // [n][ldr]
+    const int n4 = 4 * ksn;                                     // table rows: n rounded up to whole k4 steps, the extra rows zero
+    double* eLead = eLast + (size_t)n4 * ldl;                   // [n4][ldr]
     __shared__ double red_v[kMmaThreads / 32];
     __shared__ long long red_i[kMmaThreads / 32];
     __shared__ int red_n[kMmaThreads / 32];
@@ -362,31 +364,39 @@ sweep_mma_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, double bes
         if (i < n && j <= i) w = (j == i) ? 1.0 / S.L[(size_t)i * n + i] : S.L[(size_t)j * n + i];
         Wf[e] = w;
     }
-    for (int i = tid; i < n; i += kMmaThreads) {
-        al[i] = S.alpha[i];
-        sv[i] = causal ? S.sqrt_v_int[i] : 0.0;
+    for (int i = tid; i < n4; i += kMmaThreads) {
+        al[i] = i < n ? S.alpha[i] : 0.0;
+        sv[i] = (causal && i < n) ? S.sqrt_v_int[i] : 0.0;
     }
     for (int i = tid; i < n * d; i += kMmaThreads) xs[i] = S.x_int[i];
     if (SEP) {
         const double* __restrict__ gl = S.grid[d - 1];
-        for (int e = tid; e < n * p_last; e += kMmaThreads) {
+        for (int e = tid; e < n4 * p_last; e += kMmaThreads) {
             const int i = e / p_last, j = e - i * p_last;
-            const double t = gl[j] - S.x_int[i * d + d - 1];
-            eLast[i * ldl + j] = exp(-0.5 * (t * t));
+            double v = 0.0;
+            if (i < n) {
+                const double t = gl[j] - S.x_int[i * d + d - 1];
+                v = exp(-0.5 * (t * t));
+            }
+            eLast[i * ldl + j] = v;
         }
         const long long last_row = (gidx0 + cnt - 1) / p_last;
         const int nrows = (int)(last_row - row_first) + 1;
-        for (int e = tid; e < n * nrows; e += kMmaThreads) {
+        for (int e = tid; e < n4 * nrows; e += kMmaThreads) {
             const int i = e / nrows, rw = e - i * nrows;
-            long long rr = row_first + rw;
-            double r2 = 0.0;
-            for (int k = d - 2; k >= 0; --k) {
-                const long long pk = S.p[k];
-                const double t = S.grid[k][(int)(rr % pk)] - S.x_int[i * d + k];
-                r2 = fma(t, t, r2);
-                rr /= pk;
+            double v = 0.0;
+            if (i < n) {
+                long long rr = row_first + rw;
+                double r2 = 0.0;
+                for (int k = d - 2; k >= 0; --k) {
+                    const long long pk = S.p[k];
+                    const double t = S.grid[k][(int)(rr % pk)] - S.x_int[i * d + k];
+                    r2 = fma(t, t, r2);
+                    rr /= pk;
+                }
+                v = exp(-0.5 * r2);
             }
-            eLead[i * ldr + rw] = exp(-0.5 * r2);
+            eLead[i * ldr + rw] = v;
         }
     }
     __syncthreads();
@@ -440,11 +450,10 @@ sweep_mma_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, double bes
 #pragma unroll
                 for (int ks = 0; ks < kMmaKS; ++ks) {
                     a[ks] = 0.0;
-                    if (ks < ksn) {
-                        const int j = 4 * ks + q, jc = j < n ? j : n - 1;
-                        const double kv = fma(eR[jc * ldr], eL[jc * ldl], sv[jc] * svg_g);
-                        a[ks] = j < n ? kv : 0.0;
-                        mp = fma(a[ks], al[jc], mp);
+                    if (ks < ksn) {       // rows n .. n4 - 1 of the tables, of sv and of alpha are zero: k*_j = 0 there
+                        const int j = 4 * ks + q;
+                        a[ks] = fma(eR[j * ldr], eL[j * ldl], sv[j] * svg_g);
+                        mp = fma(a[ks], al[j], mp);
                     }
                 }
             } else {
@@ -553,6 +562,85 @@ sweep_mma_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, double bes
     }
 }
 
+// ---- cached posterior: EI refresh only ------------------------------------------------------------------------------------
+// After an intervention every set but the refitted one keeps mu / var (cbo_set_desc.posterior_cached) and only EI moves with
+// the incumbent: 16 B per candidate and ~150 FP64 operations (sqrt, two divisions, exp, erfc).  Inside sweep_kernel's
+// one-candidate-at-a-time loop that chain was latency-bound (32 us per 1e6 candidates, 0.5 TB/s); here a thread carries
+// kEiUnroll independent candidates through it.  Same expressions in the same order as sweep_kernel: bit-identical results.
+constexpr int kEiUnroll = 4;
+__global__ void __launch_bounds__(kSweepThreads, 6)
+ei_refresh_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, double best, double task_sign,
+                  cbo_set_best* __restrict__ tile_best) {
+    int tile;
+    const int s = find_item(sets, num_sets, kItemsSweep, blockIdx.x, tile);
+    const cbo_set_desc& S = sets[s];
+    if (sweep_class(S) != kClsCached) return;
+    const int tid = threadIdx.x;
+    __shared__ double red_v[kSweepThreads / 32];
+    __shared__ long long red_i[kSweepThreads / 32];
+    __shared__ int red_n[kSweepThreads / 32];
+    const long long loc0 = (long long)tile * CBO_SWEEP_TILE;
+    const long long left = S.g_count - loc0;
+    const int cnt = left < CBO_SWEEP_TILE ? (int)left : CBO_SWEEP_TILE;
+    const long long gidx0 = S.g_begin + loc0;
+    const double* __restrict__ gmu = S.mu + loc0;
+    const double* __restrict__ gvar = S.var + loc0;
+    double* __restrict__ gei = S.ei ? S.ei + loc0 : nullptr;
+    double* __restrict__ gacq = S.acq ? S.acq + loc0 : nullptr;
+    const double cost = S.cost_fix;
+    double val = -DBL_MAX * 2.0;  // -inf
+    long long idx = LLONG_MAX;
+    int n_nan = 0;
+#pragma unroll 1
+    for (int c0 = tid; c0 < cnt; c0 += kSweepThreads * kEiUnroll) {
+        double mu[kEiUnroll], var[kEiUnroll], ei[kEiUnroll], acq[kEiUnroll];
+#pragma unroll
+        for (int u = 0; u < kEiUnroll; ++u) {
+            const int c = c0 + u * kSweepThreads;
+            mu[u] = c < cnt ? gmu[c] : 0.0;
+            var[u] = c < cnt ? gvar[c] : 1.0;
+        }
+#pragma unroll
+        for (int u = 0; u < kEiUnroll; ++u) {
+            const double sd = sqrt(var[u]);
+            const double z = (best - mu[u]) / sd;
+            const double pdf = 0.3989422804014326779 * exp(-0.5 * z * z);
+            const double cdf = 0.5 * erfc(-z * 0.7071067811865475244);
+            ei[u] = task_sign * (sd * (z * cdf + pdf));
+            acq[u] = ei[u] / cost;
+        }
+#pragma unroll
+        for (int u = 0; u < kEiUnroll; ++u) {
+            const int c = c0 + u * kSweepThreads;
+            if (c < cnt) {
+                if (gei) gei[c] = ei[u];
+                if (gacq) gacq[c] = acq[u];
+                if (acq[u] != acq[u]) ++n_nan;
+                else if (better(acq[u], gidx0 + c, val, idx)) { val = acq[u]; idx = gidx0 + c; }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, val, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        n_nan += __shfl_xor_sync(0xffffffffu, n_nan, o);
+        if (better(ov, oi, val, idx)) { val = ov; idx = oi; }
+    }
+    if ((tid & 31) == 0) { red_v[tid >> 5] = val; red_i[tid >> 5] = idx; red_n[tid >> 5] = n_nan; }
+    __syncthreads();
+    if (tid == 0) {
+        int nan_total = red_n[0];
+        for (int w = 1; w < kSweepThreads / 32; ++w) {
+            if (better(red_v[w], red_i[w], val, idx)) { val = red_v[w]; idx = red_i[w]; }
+            nan_total += red_n[w];
+        }
+        cbo_set_best b;
+        b.value = val; b.index = idx; b.n_nan = nan_total; b.reserved = 0;
+        tile_best[blockIdx.x] = b;
+    }
+}
+
 // per-set reduction over the set's tiles (one CTA per set, fixed order)
 __global__ void __launch_bounds__(256)
 set_reduce_kernel(const cbo_set_desc* __restrict__ sets, int num_sets, const cbo_set_best* __restrict__ tile_best,
@@ -631,9 +719,10 @@ int sweep_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_s
     CBO_REQUIRE(d_tile_best && d_set_best && d_result, "cbo_sweep: NULL output pointer");
     long long total = 0;
     // per launch class (sweep_class): is there a set for it, its largest n_int, and its k* tables / workspace in doubles
-    bool any[kNumSweepClasses] = {false, false, false, false, false};
-    int nmax[kNumSweepClasses] = {1, 1, 1, 1, 1};
-    size_t tab[kNumSweepClasses] = {0, 0, 0, 0, 0};
+    bool any[kNumSweepClasses] = {};
+    int nmax[kNumSweepClasses];
+    size_t tab[kNumSweepClasses] = {};
+    for (int c = 0; c < kNumSweepClasses; ++c) nmax[c] = 1;
     for (int s = 0; s < num_sets; ++s) {
         const cbo_set_desc& S = h_sets[s];
         CBO_REQUIRE(S.n_int >= 1 && S.n_int <= CBO_MAX_NINT, "cbo_sweep: set %d n_int=%d outside [1,%d]", s, S.n_int, CBO_MAX_NINT);
@@ -671,7 +760,7 @@ int sweep_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_s
                 const cbo_set_desc& S = h_sets[s];
                 if (S.g_count <= 0 || sweep_class(S) != kClsMmaSep) continue;
                 const int pl = S.p[S.d - 1];
-                const size_t t = (size_t)S.n_int * (sweep_mma_ldl(pl) + (sweep_mma_lead_rows(pl, chunk) | 1));
+                const size_t t = (size_t)((S.n_int + 3) & ~3) * (sweep_mma_ldl(pl) + (sweep_mma_lead_rows(pl, chunk) | 1));
                 if (t > tab[kClsMmaSep]) tab[kClsMmaSep] = t;
             }
             if (chunk == 1 || mma_base + tab[kClsMmaSep] * sizeof(double) <= 160 * 1024) break;
@@ -693,6 +782,7 @@ int sweep_impl(const cbo_set_desc* h_sets, const cbo_set_desc* d_sets, int num_s
         if (any[kClsFma]) CBO_SWEEP_LAUNCH((sweep_kernel<16, false>), kSweepThreads, fma_smem(kClsFma));
         if (any[kClsMma]) CBO_SWEEP_LAUNCH((sweep_mma_kernel<false>), kMmaThreads, mma_base, , 1);
         if (any[kClsGeneric]) CBO_SWEEP_LAUNCH((sweep_kernel<0, false>), kSweepThreads, fma_smem(kClsGeneric));
+        if (any[kClsCached]) CBO_SWEEP_LAUNCH(ei_refresh_kernel, kSweepThreads, (size_t)0);
 #undef CBO_SWEEP_LAUNCH
     }
     set_reduce_kernel<<<num_sets, 256, 0, st>>>(d_sets, num_sets, d_tile_best, d_set_best);

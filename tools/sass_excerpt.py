@@ -17,7 +17,7 @@ for ln in sass.split("\n"):
 def demangle(n):
     try: return subprocess.run(["c++filt", n], capture_output=True, text=True).stdout.strip()[:150]
     except Exception: return n
-keys = [("DMMA.8x8x4", r"^(@!?U?P\d+\s+)?DMMA\.8x8x4"), ("UBLKCP (TMA bulk)", r"UBLKCP"), ("SYNCS (mbarrier)", r"SYNCS"),
+keys = [("DMMA.8x8x4", r"^(@!?U?P\d+\s+)?DMMA\.8x8x4"), ("UBLKCP (TMA bulk)", r"UBLKCP"), ("UTMALDG (TMA tensor map)", r"UTMALDG"), ("SYNCS (mbarrier)", r"SYNCS"),
         ("USETMAXREG", r"USETMAXREG"), ("LDS", r"^(@!?U?P\d+\s+)?LDS"), ("LDG", r"^(@!?U?P\d+\s+)?LDG"), ("STG", r"^(@!?U?P\d+\s+)?STG"),
         ("LDGSTS (cp.async)", r"LDGSTS"), ("LDL/STL (spills)", r"^(@!?U?P\d+\s+)?(LDL|STL)"), ("UTC*MMA / LDTM (tcgen05)", r"UTC.*MMA|LDTM")]
 print("SASS of cbo_with_oop_b200/libcbo_b200.so (sm_100a), mnemonic counts per kernel\n")
