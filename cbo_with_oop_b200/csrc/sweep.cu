@@ -3,14 +3,16 @@
 // Per candidate x of set s (one thread each; L, alpha, X_I staged once per CTA in shared memory):
 //   k*_i = exp(-.5 |x - X_I,i|^2) + sqrt(v_I,i) sqrt(v(x))        CausalRBF.K(X_I, x), causal_kernels.py:55-62
 //   mu   = m(x) + k*.alpha                                           GPy PosteriorExact._raw_predict + mean function
-//   t    = L^-1 k*  (forward substitution) ; var = (1 + v(x)) - |t|^2 + 1e-10   Kdiag :64-79, dtrtrs, Gaussian noise
+//   t    = L^-1 k* ; var = (1 + v(x)) - |t|^2 + 1e-10                Kdiag :64-79, dtrtrs, Gaussian noise
+//          (forward substitution for n <= 16 and n > 48; a DMMA product with L^-1 for 16 < n <= 48: sweep_mma_kernel)
 //   EI   = sd (u Phi(u) + phi(u)), u = (best - mu) / sd, negated for task 'max'   causal_acquisition_functions.py:33-43,85-87
 //   acq  = EI / cost(x)                                              utils.py:34, cost_functions.py:11-17
 // then a (value, index) max-reduction with np.argmax semantics (first maximum; NaN counts as -inf and is
 // tallied), per tile -> per set -> global (CBO.select_next_intervention, CBO.py:269-277: first set attaining the max).
 // The variance is not clipped (the reference does not clip either); a negative variance gives NaN.
+// Sets whose posterior is cached (cbo_set_desc.posterior_cached) only refresh EI from mu / var: ei_refresh_kernel.
 // Roofline: with the prior cached this pass is 16 B/candidate of HBM reads plus n^2/2 FMAs; it is a few
-// per cent of a post-observation sweep and the whole of a post-intervention refresh.
+// per cent of a post-observation sweep and half of a post-intervention trial.
 #include <float.h>
 #include "cbo_common.cuh"
 
